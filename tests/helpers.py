@@ -1,0 +1,44 @@
+"""Glue between the product's EnvSpec tables and the oracle's plain-array inputs (tests only)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import decode as D  # noqa: E402
+from synthesize_pregrasp_b200 import envspec as ES  # noqa: E402
+
+
+def oracle_regions(spec, states):
+    if spec.region_type == ES.REGION_MESH:
+        return D.Regions(0, states, vertices=spec.region_vertices, triangles=spec.region_triangles,
+                         normals=spec.region_normals)
+    if spec.region_type == ES.REGION_SMALL_BLOCK:
+        return D.Regions(1, states, regions=spec.block_regions, fixed_axes=spec.block_fixed_axes,
+                         surface_norm=spec.block_surface_norm)
+    return D.Regions(2, states)
+
+
+def oracle_spec(spec, states=None):
+    """EnvSpec -> the dict oracle.envsim.EnvSim takes."""
+    states = spec.dummy_states if states is None else states
+    return dict(
+        obj_shape=spec.obj_shape, obj_half=spec.obj_half, obj_hull=spec.obj_hull, obj_mass=spec.obj_mass,
+        obj_pos=spec.obj_pos, obj_quat=spec.obj_quat, obj_friction=spec.obj_friction,
+        statics=[(b.half, b.pos, b.quat, b.friction) for b in spec.statics],
+        static_names=[b.name for b in spec.statics], order=list(spec.order),
+        tip_half=[spec.tip_half_thumb, spec.tip_half_other], tip_friction=spec.tip_friction,
+        clearance_h=spec.clearance_h, clearance_walls=list(spec.clearance_walls),
+        clearance_wall_size=spec.clearance_wall_size, settle_substeps=spec.settle_substeps,
+        metric_axis=spec.metric_axis, metric_offset=spec.metric_offset,
+        regions=oracle_regions(spec, states))
+
+
+def recorded(exp):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "recorded_trajectories.npz"))
+    k = exp.replace(".", "p")
+    return dict(u=g[k + "__u"], poses=g[k + "__poses"], tips=g[k + "__tips"], env=str(g[k + "__env"]),
+                max_force=float(g[k + "__max_force"]))
