@@ -1,0 +1,251 @@
+"""bench.py -- rollout-steps/s of the MPPI rollout hot path on N GPUs of one node (see the run contract in
+DESIGN.md "Measurement").  One step = one pass of the hot path over one batch of K synthetic rollouts:
+K x (reset + 2 env steps of 1+50 substeps + settle + 2 cost evaluations).
+  python bench.py --gpus 1 --steps 3 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+  python bench.py --impl reference ...   (the CPU restatement of the reference path on the box's host cores)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {   # BASELINE.json configs: env, max force, K per GPU
+    "bookshelf_K65536": dict(env="bookshelf", force=50.0, K=65536),
+    "foodbox_K65536": dict(env="foodbox", force=20.0, K=65536),
+}
+SIGMA, KAPPA, ALPHA, N_STEPS, D = 0.8, 5.0, 1.0, 2, 48
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
+
+
+def cpu_reference_rate(env, force, n_rollouts, threads, seed=0):
+    """Times the CPU restatement (oracle/) of the same path on host cores; returns rollout-steps/s.
+    This is the one place bench.py executes oracle/ -- as the reported baseline, never as the product."""
+    import concurrent.futures as cf
+    from helpers import oracle_cost_spec, oracle_spec, oracle_weights
+    from oracle.rollout import rollout as oracle_rollout
+    from synthesize_pregrasp_b200.envspec import make_spec
+    spec = make_spec(env)
+    osd, ocs, w = oracle_spec(spec), oracle_cost_spec(spec), oracle_weights()
+    rng = np.random.RandomState(seed)
+    noise = (SIGMA * rng.randn(n_rollouts, N_STEPS, D)).astype(np.float32)
+    u = np.zeros((N_STEPS, D))
+
+    def one(k):
+        return oracle_rollout(osd, ocs, w, u, noise[k], [0, 0, 0], force)["J"]
+    t0 = time.time()
+    if threads <= 1:
+        for k in range(n_rollouts):
+            one(k)
+    else:
+        with cf.ProcessPoolExecutor(threads) as ex:
+            list(ex.map(_cpu_one, [(env, force, noise[k]) for k in range(n_rollouts)]))
+    dt = time.time() - t0
+    return n_rollouts * N_STEPS / dt, dt
+
+
+def _cpu_one(args):
+    env, force, nz = args
+    from helpers import oracle_cost_spec, oracle_spec, oracle_weights
+    from oracle.rollout import rollout as oracle_rollout
+    from synthesize_pregrasp_b200.envspec import make_spec
+    spec = make_spec(env)
+    return oracle_rollout(oracle_spec(spec), oracle_cost_spec(spec), oracle_weights(), np.zeros((N_STEPS, D)), nz, [0, 0, 0], force)["J"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bookshelf_K65536")
+    ap.add_argument("--K", type=int, default=None, help="override rollouts per GPU (profiling runs)")
+    ap.add_argument("--cpu-sample", type=int, default=None, help="rollouts in the CPU baseline sample")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.K:
+        wl["K"] = args.K
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = max(1, cores)
+        n = args.cpu_sample or max(threads, 2 * threads)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, dt = cpu_reference_rate(wl["env"], wl["force"], n, threads, seed=i)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        v = float(np.mean([x[0] for x in vals])); ms = float(np.mean([x[1] for x in vals])) * 1e3
+        sample = f"{n} rollouts of the {args.workload} workload per step on {threads} host processes (oracle/, CPU restatement of the PyBullet path; PyBullet itself is not installable here)"
+        print(json.dumps({"metric": "rollout-steps/sec", "value": v, "unit": "rollout-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "impl": "reference",
+                          "config": {"workload": args.workload, "env": wl["env"], "max_force": wl["force"], "K_per_step": n, "N": N_STEPS, "D": D},
+                          "cpu_baseline": {"value": v, "unit": "rollout-steps/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from synthesize_pregrasp_b200 import _abi
+    from synthesize_pregrasp_b200 import engine as EN
+    from synthesize_pregrasp_b200.envspec import make_spec
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    spec = make_spec(wl["env"])
+    eng = EN.RolloutEngine(spec, device=local)
+    K = wl["K"]
+    dev = torch.device("cuda", local)
+    gen = torch.Generator(device=dev).manual_seed(12367134 + rank)
+    u = torch.zeros((N_STEPS, D), dtype=torch.float64, device=dev)
+    noise = SIGMA * torch.randn((K, N_STEPS, D), generator=gen, device=dev, dtype=torch.float32)
+    noise_host = noise.cpu().pin_memory()
+    path = [0, 0]
+    L = _abi.lib()
+
+    def step_device():
+        J = eng.rollout(u, noise, path, wl["force"])
+        part = EN.mppi_update(J, noise, None, KAPPA, ALPHA, apply=False, want_partial=True)
+        if world > 1:
+            got = [torch.empty_like(part) for _ in range(world)]
+            dist.all_gather(got, part)
+        return J
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = L.pg_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step_device()
+        ev[i + 1].record()
+    barrier()
+    launches = int(L.pg_launch_count() - l0)
+    total_ms = ev[0].elapsed_time(ev[-1])
+    # dominant-kernel timing: physics and cost stages separately, CUDA events on the launching stream
+    out = eng.physics(u, noise, path, wl["force"])
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    torch.cuda.synchronize()
+    e0.record(); out = eng.physics(u, noise, path, wl["force"]); e1.record()
+    logit = eng.cost(out["pose"], out["fins"]); e2.record()
+    torch.cuda.synchronize()
+    phys_ms, cost_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    # e2e: host buffers in, host J out, through the plugin-facing C-ABI call
+    nh = noise_host.numpy(); uh = np.zeros((N_STEPS, D))
+    eng.rollout_host(uh, nh, path, wl["force"])
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        Jh = eng.rollout_host(uh, nh, path, wl["force"])
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    sampler.stop_flag = True
+    sampler.join(2)
+
+    t = torch.tensor([total_ms, e2e_s * 1e3, phys_ms, cost_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, phys_ms, cost_ms = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = total_ms / args.steps
+    units = K * world * N_STEPS
+    value = units / (ms_per_step * 1e-3)
+    peaks = _peaks()
+    substeps = spec.substeps_per_rollout
+    # dominant kernel: the slower of physics / cost; roofline figures per DESIGN.md "Measurement"
+    FLOP_PER_EVAL = 164.9e6          # algorithmic FLOPs of one score evaluation at P=2048
+    FP32_PEAK_TF = 148 * 128 * 2 * 1.965e9 / 1e12
+    if cost_ms >= phys_ms:
+        ach = FLOP_PER_EVAL * K * N_STEPS / (cost_ms * 1e-3) / 1e12
+        roof = {"kernel": "pcn_kernel (fused cost)", "bound": "tensor", "achieved": ach, "peak": peaks["bf16"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16"], "traffic": None, "peak_source": peaks["src"],
+                "note": f"fp32 FFMA implementation this round; vs nominal fp32 FFMA peak {FP32_PEAK_TF:.1f} TF/s frac {ach / FP32_PEAK_TF:.3f}"}
+    else:
+        flop_sub = 90e3                # SURVEY 8(d) estimate of one physics substep
+        ach = flop_sub * substeps * K / (phys_ms * 1e-3) / 1e12
+        F64_PEAK_TF = FP32_PEAK_TF / 2
+        roof = {"kernel": "rollout_kernel (physics)", "bound": "fp64-issue", "achieved": ach, "peak": F64_PEAK_TF, "unit": "TFLOP/s",
+                "frac": ach / F64_PEAK_TF, "traffic": None, "peak_source": "nominal fp64 DFMA rate (latency/issue-bound kernel; HBM and tensor rooflines do not bind it)"}
+    cpu_n = args.cpu_sample or 8
+    cpu_v, cpu_dt = cpu_reference_rate(wl["env"], wl["force"], cpu_n, 1)
+    line = {"metric": "rollout-steps/sec", "value": value, "unit": "rollout-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "env": wl["env"], "max_force": wl["force"], "K_per_gpu": K, "N": N_STEPS, "D": D,
+                       "substeps_per_rollout": substeps, "sigma": SIGMA, "l2": f"inputs+state {K * (N_STEPS * D * 4 + 21408) / 1e6:.0f} MB > 126 MB L2"},
+            "substeps_per_s": K * world * substeps / (ms_per_step * 1e-3), "mppi_iters_per_s": 1e3 / ms_per_step,
+            "stage_ms": {"physics": phys_ms, "cost": cost_ms},
+            "roofline": roof,
+            "cpu_baseline": {"value": cpu_v, "unit": "rollout-steps/s", "cores": 1, "kind": "port",
+                             "sample": f"{cpu_n} rollouts of the same workload, 1 process, oracle/ (CPU restatement; Python-driven like the reference) in {cpu_dt:.1f} s"},
+            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "rollout-steps/s", "h2d_bytes_per_step": int(nh.nbytes + uh.nbytes),
+                    "d2h_bytes_per_step": int(K * 8)},
+            "gpu_launches": launches, "clocks": sampler.summary(), "host_cores": cores}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,140 @@
+/* pregrasp_b200 -- C ABI of the B200-native MPPI rollout path of synthesize_pregrasp.
+ *
+ * The reference (Python) has no FFI seam; these entry points are what a binding for its hot path binds.
+ * Each one names the reference interface it replaces (paths relative to the reference root).
+ * Conventions: every function returns 0 on success, a PG_ERR_* code otherwise; pg_last_error() gives the
+ * text of the last failure on the calling thread.  No exceptions cross the ABI.  Pointers named *_dev are
+ * device pointers on the handle's GPU, *_host are host pointers.  `stream` is a cudaStream_t passed as
+ * void* (NULL = default stream); *_dev calls are asynchronous on that stream.  Handles are not thread-safe;
+ * independent handles are.  Quaternions are xyzw.
+ */
+#ifndef PREGRASP_B200_H
+#define PREGRASP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_ERR_INVALID 1      /* bad argument */
+#define PG_ERR_CUDA 2         /* CUDA runtime error (text in pg_last_error) */
+#define PG_ERR_UNSUPPORTED 3  /* valid reference feature not built yet (hull / cylinder objects) */
+
+#define PG_ACTION_DIM 48      /* 2 fingers x (7 knots x 3 + 2 position params + on/off), plate_env:145-147 */
+#define PG_CONTROL_SKIP 50    /* plate_env:51 */
+#define PG_MAX_STATICS 4
+
+typedef struct PgBox {        /* static box: setup_pybullet.py create_* wall / plane.urdf floor */
+  double half[3], pos[3], quat[4], friction;
+  int32_t compound;           /* 1 for the URDF floor (collision origin offset keeps it a compound shape) */
+  int32_t pad;
+} PgBox;
+
+typedef struct PgScoreWeights { /* neurals/network.py:434-441 LargeScoreFunction(num_fingers=2, latent_dim=20, df) */
+  const float *conv1_w, *conv1_b; /* [32,4], [32]   */
+  const float *conv2_w, *conv2_b; /* [64,32], [64]  */
+  const float *conv3_w, *conv3_b; /* [256,128], [256] */
+  const float *conv4_w, *conv4_b; /* [20,256], [20] */
+  const float *fc1_w, *fc1_b;     /* [512,26], [512] */
+  const float *fc2_w, *fc2_b;     /* [512,512], [512] */
+  const float *fc3_w, *fc3_b;     /* [256,512], [256] */
+  const float *out_w, *out_b;     /* [1,256], [1] */
+} PgScoreWeights;
+
+typedef struct PgEnvSpec {     /* the constructor kwargs + literals of envs/<env>_contact_graph_env.py */
+  /* dynamic object */
+  int32_t obj_shape;           /* 0 box, 1 convex hull, 2 z-cylinder */
+  int32_t n_hull;
+  double obj_half[3];
+  const double* hull;          /* [n_hull,3] or NULL */
+  double obj_mass, obj_pos[3], obj_quat[4], obj_friction;
+  /* static scene, creation order */
+  int32_t n_static, floor_index;
+  PgBox statics[PG_MAX_STATICS];
+  /* fingertips (thumb, index) */
+  double tip_half[2][3], tip_friction;
+  /* env logic */
+  double clearance_h, clearance_wall_size[3];
+  int32_t n_clear_walls, clear_walls[2];
+  int32_t project_uses_clearance; /* 0: plate rule point.z > CLEARANCE_H (plate_env:669); 1: checkClearance(point) */
+  int32_t settle_substeps, metric_axis;
+  double metric_offset;
+  /* contact regions + contact state graph */
+  int32_t region_type, n_regions, n_states, pad0;
+  const double* tri_v;         /* mesh regions [n_regions,3,3] */
+  const double* region_n;      /* [n_regions,3] */
+  const double* block_r;       /* small-block regions [n_regions,6] */
+  const int32_t* block_axis;   /* [n_regions] */
+  const int32_t* csg;          /* [n_states,2] 1-based region ids */
+  /* cost: object cloud, de-occlusion boxes, distance-field meshes, score network */
+  int32_t n_cloud, n_crop;
+  const double* cloud;         /* [n_cloud,3] object frame */
+  double crop[2][2][3];        /* (min,max) world AABBs, union */
+  int32_t n_dist_box, n_dist_tri;
+  double dist_box[4][2][3];    /* (min,max) corners of the distance-field boxes */
+  const double* dist_tri;      /* [n_dist_tri,3,3] or NULL */
+  PgScoreWeights weights;
+} PgEnvSpec;
+
+typedef struct PgEnv PgEnv;
+
+const char* pg_last_error(void);
+const char* pg_version(void);
+
+/* replaces env_fn(render=False, device=..., **kwargs) in the worker, stoch_traj_opt.py:113 */
+int pg_env_create(const PgEnvSpec* spec, int device, PgEnv** out);
+int pg_env_destroy(PgEnv* env);
+
+/* replaces the worker's "control" branch, stoch_traj_opt.py:119-136: K rollouts of N env steps from the
+ * post-reset state with actions u[j] + noise[k,j], cost J[k] = sum_j -reward (reward = 100 x score logit).
+ * u_dev [N,48] f64; noise_dev [K,N,48] f32 or NULL (=> K copies of u, replay_traj :233-247);
+ * path_host [N] contact-state ids; J_dev [K] f64; metric_dev [K] f64 or NULL (info["metric"]);
+ * trace_dev [K,N*50,7] f64 or NULL (object pose at the start of every control substep, model_test.py:124-135). */
+int pg_rollout(PgEnv* env, const double* u_dev, const float* noise_dev, int K, int N, const int32_t* path_host,
+               double max_force, double* J_dev, double* metric_dev, double* trace_dev, void* stream);
+
+/* same call with HOST buffers: copies in, runs, copies J/metric back, synchronises (the plugin-facing form) */
+int pg_rollout_host(PgEnv* env, const double* u_host, const float* noise_host, int K, int N,
+                    const int32_t* path_host, double max_force, double* J_host, double* metric_host,
+                    double* trace_host);
+
+/* the two stages of pg_rollout, exposed for tests and profiling */
+int pg_physics(PgEnv* env, const double* u_dev, const float* noise_dev, int K, int N, const int32_t* path_host,
+               double max_force, double* pose_dev /*[K,N,7]*/, double* fins_dev /*[K,N,2,3]*/,
+               double* metric_dev, double* trace_dev, int32_t* iters_dev, void* stream);
+/* calc_reward_value_stage_one, plate_env:393-437: B evaluations -> logits */
+int pg_cost(PgEnv* env, const double* pose_dev /*[B,7]*/, const double* fins_dev /*[B,2,3]*/, int B,
+            float* logit_dev /*[B]*/, void* stream);
+/* LargeScoreFunction.pred_score on explicit inputs (neurals/network.py:443-455): pts [B,P,3] f32, df [B,P] f32,
+ * mask [B,P] u8 (0 = cropped away), grasp [B,6] f32 -> logit [B]; what generate_csg.py:108-130 batches */
+int pg_score(PgEnv* env, const float* pts_dev, const float* df_dev, const uint8_t* mask_dev, const float* grasp_dev,
+             int B, int P, float* logit_dev, void* stream);
+
+/* replaces stoch_traj_opt.py:195-204.  J [K] f64, noise [K,N,D] f32, u_inout [N,D] f64.
+ * partial_dev (nullable) receives (min J, sum w, sum J, sum w*noise[N*D]) = 3+N*D doubles for the multi-GPU merge;
+ * when apply != 0 the update u += alpha * sum(w noise)/sum(w) is applied in place. */
+int pg_mppi_update(const double* J_dev, const float* noise_dev, int K, int N, int D, double kappa, double alpha,
+                   double* u_inout_dev, double* partial_dev, int apply, void* stream);
+/* merge G partials (host side of the per-iteration exchange) and apply: u += alpha * V/S */
+int pg_mppi_merge_apply(const double* partials_host /*[G,3+N*D]*/, int G, int N, int D, double kappa, double alpha,
+                        double* u_inout_host);
+
+/* utils/dyn_feasibility_check.py:153-235 simple_check_dyn_feasible: pts/nrm [B,M,3] f64, count [B] (<= M) or NULL */
+int pg_dyn_feasible_simple(const double* pts_dev, const double* nrm_dev, const int32_t* count_dev, int B, int M,
+                           uint8_t* out_dev, void* stream);
+/* all C(P,3) triples of a cloud (find_dynamically_feasible_contacts :239-303 with the simple criterion and the
+ * pairwise min-distance prefilter :260-265); triple index range [first,last) for multi-GPU partitioning.
+ * triples_out_dev [cap,3] i32 (nullable), count_dev [1] u64 */
+int pg_dyn_sweep_simple(const double* cloud_pts_dev, const double* cloud_nrm_dev, int P, double min_dist,
+                        uint64_t first, uint64_t last, int32_t* triples_out_dev, uint64_t cap,
+                        unsigned long long* count_dev, void* stream);
+
+/* diagnostics: number of kernel launches issued through this library since load */
+uint64_t pg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

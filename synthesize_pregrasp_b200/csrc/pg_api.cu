@@ -1,0 +1,226 @@
+// C ABI (include/pregrasp_b200.h): handle management, constant upload, host-buffer wrappers.
+#include <math.h>
+#include <string.h>
+#include <atomic>
+#include <vector>
+#include "pg_internal.h"
+#include "pg_envbuild.h"
+
+namespace pg {
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+void set_error(const std::string& s) { g_err = s; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return PG_ERR_CUDA;
+}
+void count_launch() { g_launches++; }
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" const char* pg_last_error(void) { return g_err.c_str(); }
+extern "C" const char* pg_version(void) { return "pregrasp_b200 0.1 (sm_100a)"; }
+extern "C" uint64_t pg_launch_count(void) { return g_launches.load(); }
+
+
+static void pk_quat_to_matrix(const double* q_xyzw, double* R) {
+  double x = q_xyzw[0], y = q_xyzw[1], z = q_xyzw[2], w = q_xyzw[3];
+  double two_s = 2.0 / (w * w + x * x + y * y + z * z);
+  R[0] = 1 - two_s * (y * y + z * z); R[1] = two_s * (x * y - z * w); R[2] = two_s * (x * z + y * w);
+  R[3] = two_s * (x * y + z * w); R[4] = 1 - two_s * (x * x + z * z); R[5] = two_s * (y * z - x * w);
+  R[6] = two_s * (x * z - y * w); R[7] = two_s * (y * z + x * w); R[8] = 1 - two_s * (x * x + y * y);
+}
+
+struct Blob {
+  std::vector<unsigned char> h;
+  size_t add(const void* p, size_t bytes) {
+    size_t off = (h.size() + 255) & ~size_t(255);
+    h.resize(off + bytes);
+    memcpy(h.data() + off, p, bytes);
+    return off;
+  }
+};
+
+extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
+  if (!sp || !out) { set_error("pg_env_create: null argument"); return PG_ERR_INVALID; }
+  if (sp->obj_shape != SHAPE_BOX) { set_error("pg_env_create: only box objects are built in this round (hull/cylinder: GJK path pending)"); return PG_ERR_UNSUPPORTED; }
+  if (sp->n_static < 1 || sp->n_static > MAX_STATICS || sp->n_regions > MAX_REGIONS || sp->n_states > MAX_STATES ||
+      sp->n_cloud != P_CLOUD || sp->n_crop < 1 || sp->n_crop > 2 || sp->n_dist_box > 4 || !sp->cloud || !sp->csg) {
+    set_error("pg_env_create: spec out of supported bounds"); return PG_ERR_INVALID;
+  }
+  int ndev = 0;
+  PG_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { set_error("pg_env_create: no such CUDA device"); return PG_ERR_INVALID; }
+  PG_CUDA(cudaSetDevice(device));
+  PgEnv* e = new PgEnv();
+  memset(e, 0, sizeof(PgEnv));
+  e->device = device;
+  EnvDev& E = e->host_env;
+  { std::string err; int rc = build_envdev(sp, E, err); if (rc) { set_error("pg_env_create: " + err); delete e; return rc; } }
+  // ---- cost constants
+  const PgScoreWeights& W = sp->weights;
+  if (!W.conv1_w || !W.out_b) { set_error("pg_env_create: score weights missing"); delete e; return PG_ERR_INVALID; }
+  std::vector<float> a1((size_t)P_CLOUD * C1), w1d(C1), w2t(C1 * C2), w3at(C2 * C3), w3bt(C2 * C3);
+  for (int p = 0; p < P_CLOUD; p++) {
+    float x = (float)sp->cloud[3 * p], y = (float)sp->cloud[3 * p + 1], z = (float)sp->cloud[3 * p + 2];
+    for (int j = 0; j < C1; j++) {
+      float v = W.conv1_b[j];
+      v = fmaf(W.conv1_w[4 * j], x, v); v = fmaf(W.conv1_w[4 * j + 1], y, v); v = fmaf(W.conv1_w[4 * j + 2], z, v);
+      a1[(size_t)p * C1 + j] = v;
+    }
+  }
+  for (int j = 0; j < C1; j++) w1d[j] = W.conv1_w[4 * j + 3];
+  for (int c = 0; c < C2; c++) for (int j = 0; j < C1; j++) w2t[j * C2 + c] = W.conv2_w[c * C1 + j];
+  for (int o = 0; o < C3; o++) for (int k = 0; k < C2; k++) { w3at[k * C3 + o] = W.conv3_w[o * 2 * C2 + k]; w3bt[k * C3 + o] = W.conv3_w[o * 2 * C2 + C2 + k]; }
+  Blob b;
+  size_t o_env = b.add(&E, sizeof(EnvDev));
+  size_t o_cloud = b.add(sp->cloud, sizeof(double) * 3 * P_CLOUD);
+  size_t o_a1 = b.add(a1.data(), a1.size() * 4), o_w1d = b.add(w1d.data(), C1 * 4), o_w2t = b.add(w2t.data(), w2t.size() * 4);
+  size_t o_b2 = b.add(W.conv2_b, C2 * 4), o_w3at = b.add(w3at.data(), w3at.size() * 4), o_w3bt = b.add(w3bt.data(), w3bt.size() * 4);
+  size_t o_b3 = b.add(W.conv3_b, C3 * 4), o_w4 = b.add(W.conv4_w, C4 * C3 * 4), o_b4 = b.add(W.conv4_b, C4 * 4);
+  size_t o_f1w = b.add(W.fc1_w, F1 * LAT * 4), o_f1b = b.add(W.fc1_b, F1 * 4), o_f2w = b.add(W.fc2_w, F2 * F1 * 4), o_f2b = b.add(W.fc2_b, F2 * 4);
+  size_t o_f3w = b.add(W.fc3_w, F3 * F2 * 4), o_f3b = b.add(W.fc3_b, F3 * 4), o_ow = b.add(W.out_w, F3 * 4), o_ob = b.add(W.out_b, 4);
+  size_t o_w1 = b.add(W.conv1_w, C1 * 4 * 4), o_b1 = b.add(W.conv1_b, C1 * 4);
+  size_t o_tri = sp->n_dist_tri > 0 ? b.add(sp->dist_tri, sizeof(double) * 9 * sp->n_dist_tri) : 0;
+  unsigned char* d = nullptr;
+  cudaError_t ce = cudaMalloc(&d, b.h.size());
+  if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "cudaMalloc(env constants)"); }
+  ce = cudaMemcpy(d, b.h.data(), b.h.size(), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) { cudaFree(d); delete e; return cuda_fail(ce, "cudaMemcpy(env constants)"); }
+  e->blob = d;
+  e->dev_env = reinterpret_cast<EnvDev*>(d + o_env);
+  CostDev& c = e->cost;
+  c.cloud = reinterpret_cast<const double*>(d + o_cloud);
+#define FP(off) reinterpret_cast<const float*>(d + (off))
+  c.a1 = FP(o_a1); c.w1d = FP(o_w1d); c.w2t = FP(o_w2t); c.b2 = FP(o_b2); c.w3at = FP(o_w3at); c.w3bt = FP(o_w3bt);
+  c.b3 = FP(o_b3); c.w4 = FP(o_w4); c.b4 = FP(o_b4); c.fc1_w = FP(o_f1w); c.fc1_b = FP(o_f1b); c.fc2_w = FP(o_f2w);
+  c.fc2_b = FP(o_f2b); c.fc3_w = FP(o_f3w); c.fc3_b = FP(o_f3b); c.out_w = FP(o_ow); c.out_b = FP(o_ob);
+  c.w1 = FP(o_w1); c.b1 = FP(o_b1);
+#undef FP
+  c.n_cloud = P_CLOUD; c.n_crop = sp->n_crop; c.n_dist_box = sp->n_dist_box; c.n_dist_tri = sp->n_dist_tri;
+  memcpy(c.crop, sp->crop, sizeof(c.crop));
+  memcpy(c.dist_box, sp->dist_box, sizeof(c.dist_box));
+  c.dist_tri = sp->n_dist_tri > 0 ? reinterpret_cast<const double*>(d + o_tri) : nullptr;
+  c.clearance_h = sp->clearance_h; c.project_uses_clearance = sp->project_uses_clearance;
+  c.clear_n = sp->n_clear_walls;
+  for (int w = 0; w < sp->n_clear_walls && w < 2; w++) {
+    const PgBox& bx = sp->statics[sp->clear_walls[w]];
+    for (int i = 0; i < 3; i++) c.clear_pos[w][i] = bx.pos[i];
+    pk_quat_to_matrix(bx.quat, c.clear_R[w]);
+  }
+  for (int i = 0; i < 3; i++) c.clear_size[i] = sp->clearance_wall_size[i];
+  *out = e;
+  return PG_OK;
+}
+
+extern "C" int pg_env_destroy(PgEnv* e) {
+  if (!e) return PG_OK;
+  cudaSetDevice(e->device);
+  cudaFree(e->blob); cudaFree(e->pose); cudaFree(e->fins); cudaFree(e->logit); cudaFree(e->latent); cudaFree(e->path_dev);
+  cudaFree(e->u_stage); cudaFree(e->noise_stage); cudaFree(e->J_stage); cudaFree(e->metric_stage); cudaFree(e->trace_stage);
+  delete e;
+  return PG_OK;
+}
+
+static int ensure_scratch(PgEnv* e, size_t evals) {
+  if (e->cap_evals >= evals && e->path_dev) return PG_OK;
+  cudaFree(e->pose); cudaFree(e->fins); cudaFree(e->logit); cudaFree(e->latent);
+  e->pose = e->fins = nullptr; e->logit = e->latent = nullptr;
+  PG_CUDA(cudaMalloc(&e->pose, evals * 7 * sizeof(double)));
+  PG_CUDA(cudaMalloc(&e->fins, evals * 6 * sizeof(double)));
+  PG_CUDA(cudaMalloc(&e->logit, evals * sizeof(float)));
+  PG_CUDA(cudaMalloc(&e->latent, evals * LAT * sizeof(float)));
+  if (!e->path_dev) PG_CUDA(cudaMalloc(&e->path_dev, 64 * sizeof(int)));
+  e->cap_evals = evals;
+  return PG_OK;
+}
+
+static int check_rollout_args(PgEnv* e, const double* u, int K, int N, const int32_t* path) {
+  if (!e || !u || !path || K <= 0 || N <= 0 || N > 32) { set_error("pg_rollout: bad arguments"); return PG_ERR_INVALID; }
+  for (int j = 0; j < N; j++) if (path[j] < 0 || path[j] >= e->host_env.n_states) { set_error("pg_rollout: path state out of range"); return PG_ERR_INVALID; }
+  return PG_OK;
+}
+
+extern "C" int pg_physics(PgEnv* e, const double* u_dev, const float* noise_dev, int K, int N, const int32_t* path_host,
+                          double max_force, double* pose_dev, double* fins_dev, double* metric_dev, double* trace_dev,
+                          int32_t* iters_dev, void* stream) {
+  int rc = check_rollout_args(e, u_dev, K, N, path_host);
+  if (rc) return rc;
+  if (!pose_dev || !fins_dev) { set_error("pg_physics: null output"); return PG_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  PG_CUDA(cudaSetDevice(e->device));
+  rc = ensure_scratch(e, (size_t)K * N);
+  if (rc) return rc;
+  PG_CUDA(cudaMemcpyAsync(e->path_dev, path_host, N * sizeof(int), cudaMemcpyHostToDevice, st));
+  return launch_physics(e, u_dev, noise_dev, K, N, e->path_dev, max_force, pose_dev, fins_dev, metric_dev, trace_dev, iters_dev, st);
+}
+
+extern "C" int pg_cost(PgEnv* e, const double* pose_dev, const double* fins_dev, int B, float* logit_dev, void* stream) {
+  if (!e || !pose_dev || !fins_dev || !logit_dev || B <= 0) { set_error("pg_cost: bad arguments"); return PG_ERR_INVALID; }
+  PG_CUDA(cudaSetDevice(e->device));
+  int rc = ensure_scratch(e, (size_t)B);
+  if (rc) return rc;
+  return launch_cost(e, pose_dev, fins_dev, B, e->latent, logit_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pg_score(PgEnv* e, const float* pts_dev, const float* df_dev, const uint8_t* mask_dev, const float* grasp_dev,
+                        int B, int P, float* logit_dev, void* stream) {
+  if (!e || !pts_dev || !df_dev || !grasp_dev || !logit_dev || B <= 0 || P <= 0) { set_error("pg_score: bad arguments"); return PG_ERR_INVALID; }
+  PG_CUDA(cudaSetDevice(e->device));
+  int rc = ensure_scratch(e, (size_t)B);
+  if (rc) return rc;
+  return launch_score(e, pts_dev, df_dev, mask_dev, grasp_dev, B, P, e->latent, logit_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pg_rollout(PgEnv* e, const double* u_dev, const float* noise_dev, int K, int N, const int32_t* path_host,
+                          double max_force, double* J_dev, double* metric_dev, double* trace_dev, void* stream) {
+  int rc = check_rollout_args(e, u_dev, K, N, path_host);
+  if (rc) return rc;
+  if (!J_dev) { set_error("pg_rollout: null J"); return PG_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  PG_CUDA(cudaSetDevice(e->device));
+  rc = ensure_scratch(e, (size_t)K * N);
+  if (rc) return rc;
+  PG_CUDA(cudaMemcpyAsync(e->path_dev, path_host, N * sizeof(int), cudaMemcpyHostToDevice, st));
+  rc = launch_physics(e, u_dev, noise_dev, K, N, e->path_dev, max_force, e->pose, e->fins, metric_dev, trace_dev, nullptr, st);
+  if (rc) return rc;
+  rc = launch_cost(e, e->pose, e->fins, K * N, e->latent, e->logit, st);
+  if (rc) return rc;
+  return launch_accumulate_cost(e->logit, K, N, J_dev, st);
+}
+
+extern "C" int pg_rollout_host(PgEnv* e, const double* u_host, const float* noise_host, int K, int N,
+                               const int32_t* path_host, double max_force, double* J_host, double* metric_host,
+                               double* trace_host) {
+  int rc = check_rollout_args(e, u_host, K, N, path_host);
+  if (rc) return rc;
+  if (!J_host) { set_error("pg_rollout_host: null J"); return PG_ERR_INVALID; }
+  PG_CUDA(cudaSetDevice(e->device));
+  if (e->cap_stage_K < (size_t)K) {
+    cudaFree(e->noise_stage); cudaFree(e->J_stage); cudaFree(e->metric_stage); cudaFree(e->u_stage);
+    e->noise_stage = nullptr; e->J_stage = e->metric_stage = e->u_stage = nullptr;
+    PG_CUDA(cudaMalloc(&e->noise_stage, (size_t)K * 32 * ADIM * sizeof(float)));
+    PG_CUDA(cudaMalloc(&e->J_stage, (size_t)K * sizeof(double)));
+    PG_CUDA(cudaMalloc(&e->metric_stage, (size_t)K * sizeof(double)));
+    PG_CUDA(cudaMalloc(&e->u_stage, 32 * ADIM * sizeof(double)));
+    e->cap_stage_K = K;
+  }
+  size_t tr = trace_host ? (size_t)K * N * SKIP * 7 : 0;
+  if (tr > e->cap_stage_trace) {
+    cudaFree(e->trace_stage); e->trace_stage = nullptr;
+    PG_CUDA(cudaMalloc(&e->trace_stage, tr * sizeof(double)));
+    e->cap_stage_trace = tr;
+  }
+  cudaStream_t st = 0;
+  PG_CUDA(cudaMemcpyAsync(e->u_stage, u_host, (size_t)N * ADIM * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (noise_host) PG_CUDA(cudaMemcpyAsync(e->noise_stage, noise_host, (size_t)K * N * ADIM * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = pg_rollout(e, e->u_stage, noise_host ? e->noise_stage : nullptr, K, N, path_host, max_force, e->J_stage,
+                  metric_host ? e->metric_stage : nullptr, trace_host ? e->trace_stage : nullptr, st);
+  if (rc) return rc;
+  PG_CUDA(cudaMemcpyAsync(J_host, e->J_stage, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (metric_host) PG_CUDA(cudaMemcpyAsync(metric_host, e->metric_stage, (size_t)K * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (trace_host) PG_CUDA(cudaMemcpyAsync(trace_host, e->trace_stage, tr * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PG_CUDA(cudaStreamSynchronize(st));
+  return PG_OK;
+}

@@ -1,0 +1,61 @@
+// Host-side construction of the device constant block from the ABI spec (no CUDA calls: also used by the
+// CPU logic tests, which compile pg_rollout.cuh for the host).
+#pragma once
+#include <math.h>
+#include <string.h>
+#include <string>
+#include "../../include/pregrasp_b200.h"
+#include "pg_env.cuh"
+
+namespace pg {
+
+static inline double box_radius(const double* h) { return sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]); }
+
+static inline int build_envdev(const PgEnvSpec* sp, EnvDev& E, std::string& err) {
+  if (sp->obj_shape != SHAPE_BOX) { err = "only box objects are built in this round (hull/cylinder: GJK path pending)"; return PG_ERR_UNSUPPORTED; }
+  if (sp->n_static < 1 || sp->n_static > MAX_STATICS || sp->n_regions > MAX_REGIONS || sp->n_states > MAX_STATES || !sp->csg) {
+    err = "spec out of supported bounds"; return PG_ERR_INVALID;
+  }
+  memset(&E, 0, sizeof(EnvDev));
+  // ---- PyBullet server defaults confirmed by the recorded trajectories
+  E.dt = 1.0 / 250.0; E.gravity_z = -10.0; E.erp = 0.2; E.erp2 = 0.08; E.slop = 1e-5; E.residual_threshold = 1e-7;
+  E.lin_damping = 0.04; E.ang_damping = 0.04; E.breaking_factor = 0.02; E.aabb_margin = 0.02; E.max_coord_vel = 100.0;
+  E.default_max_impulse = 500.0; E.iterations = 50;
+  E.obj_shape = sp->obj_shape; E.n_hull = 0;
+  for (int i = 0; i < 3; i++) { E.obj_half[i] = sp->obj_half[i]; E.obj_pos[i] = sp->obj_pos[i]; }
+  for (int i = 0; i < 4; i++) E.obj_quat[i] = sp->obj_quat[i];
+  E.obj_mass = sp->obj_mass; E.obj_friction = sp->obj_friction; E.obj_margin = 0.001;
+  {
+    double lx = 2 * E.obj_half[0], ly = 2 * E.obj_half[1], lz = 2 * E.obj_half[2], m = E.obj_mass;   // btBoxShape::calculateLocalInertia
+    E.obj_inertia[0] = m / 12.0 * (ly * ly + lz * lz); E.obj_inertia[1] = m / 12.0 * (lx * lx + lz * lz); E.obj_inertia[2] = m / 12.0 * (lx * lx + ly * ly);
+    E.obj_radius_bs = box_radius(E.obj_half);
+  }
+  E.n_static = sp->n_static; E.floor_index = sp->floor_index;
+  for (int s = 0; s < sp->n_static; s++) {
+    memcpy(&E.statics[s], &sp->statics[s], sizeof(PgBox));
+    E.static_radius_bs[s] = box_radius(sp->statics[s].half);
+  }
+  E.tip_mass = 0.01; E.tip_friction = sp->tip_friction;
+  for (int f = 0; f < 2; f++) {
+    for (int i = 0; i < 3; i++) E.tip_half[f][i] = sp->tip_half[f][i];
+    double lx = 2 * E.tip_half[f][0], ly = 2 * E.tip_half[f][1], lz = 2 * E.tip_half[f][2], m = E.tip_mass;
+    E.tip_inertia[f][0] = m / 12.0 * (ly * ly + lz * lz); E.tip_inertia[f][1] = m / 12.0 * (lx * lx + lz * lz); E.tip_inertia[f][2] = m / 12.0 * (lx * lx + ly * ly);
+    E.tip_radius_bs[f] = box_radius(E.tip_half[f]);
+  }
+  E.clearance_h = sp->clearance_h;
+  for (int i = 0; i < 3; i++) E.clearance_wall_size[i] = sp->clearance_wall_size[i];
+  E.n_clear_walls = sp->n_clear_walls; E.clear_walls[0] = sp->clear_walls[0]; E.clear_walls[1] = sp->clear_walls[1];
+  E.settle_substeps = sp->settle_substeps; E.metric_axis = sp->metric_axis; E.metric_offset = sp->metric_offset;
+  E.region_type = sp->region_type; E.n_regions = sp->n_regions; E.n_states = sp->n_states;
+  if (sp->tri_v) memcpy(E.tri_v, sp->tri_v, sizeof(double) * 9 * sp->n_regions);
+  if (sp->region_n) memcpy(E.region_n, sp->region_n, sizeof(double) * 3 * sp->n_regions);
+  if (sp->block_r) memcpy(E.block_r, sp->block_r, sizeof(double) * 6 * sp->n_regions);
+  if (sp->block_axis) for (int i = 0; i < sp->n_regions; i++) E.block_axis[i] = sp->block_axis[i];
+  for (int i = 0; i < sp->n_states * 2; i++) E.csg[i] = sp->csg[i];
+  E.bottle_radius = 0.045; E.bottle_length = 0.22;
+  for (int i = 0; i < NKNOT; i++) E.interp_xp[i] = (i == NKNOT - 1) ? 50.0 : (double)i * (50.0 / 6.0);   // np.linspace(0,50,7)
+
+  return PG_OK;
+}
+
+}  // namespace pg

@@ -1,0 +1,66 @@
+// Host-side definition of the env handle shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/pregrasp_b200.h"
+#include "pg_env.cuh"
+
+namespace pg {
+
+enum { P_CLOUD = 2048, C1 = 32, C2 = 64, C3 = 256, C4 = 20, LAT = 26, F1 = 512, F2 = 512, F3 = 256 };
+
+struct CostDev {                 // device pointers of the cost stage constants
+  const double* cloud;           // [P,3] f64
+  const float* a1;               // [P,32]  W1[:, :3] xyz + b1  (rollout-invariant part of conv1)
+  const float* w1d;              // [32]    W1[:, 3]
+  const float* w2t;              // [32,64] conv2 weight transposed
+  const float* b2;               // [64]
+  const float* w3at;             // [64,256] conv3 weight, point half, transposed
+  const float* w3bt;             // [64,256] conv3 weight, global-feature half, transposed
+  const float* b3;               // [256]
+  const float* w4;               // [20,256]
+  const float* b4;               // [20]
+  const float *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b, *out_w, *out_b;
+  const float* w1;               // [32,4] full conv1 (pg_score path with explicit points)
+  const float* b1;
+  int n_cloud, n_crop, n_dist_box, n_dist_tri;
+  double crop[2][2][3];
+  double dist_box[4][2][3];
+  const double* dist_tri;
+  double clearance_h;
+  int project_uses_clearance;     // 1: checkClearance(local point) incl. the walls (bookshelf_graph_env.py:683-689)
+  int clear_n;
+  double clear_pos[2][3], clear_R[2][9], clear_size[3];
+};
+
+}  // namespace pg
+
+struct PgEnv {
+  int device;
+  pg::EnvDev host_env;
+  pg::EnvDev* dev_env;
+  pg::CostDev cost;
+  void* blob;                    // one allocation holding every constant table
+  // scratch (grown on demand)
+  double *pose, *fins;           // [K,N,7], [K,N,2,3]
+  float* logit;                  // [K*N]
+  float* latent;                 // [K*N,26]
+  int* path_dev;
+  size_t cap_evals;
+  double *u_stage; float* noise_stage; double *J_stage, *metric_stage, *trace_stage;   // pg_rollout_host staging
+  size_t cap_stage_K, cap_stage_trace;
+};
+
+namespace pg {
+void set_error(const std::string& s);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch();
+#define PG_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return pg::cuda_fail(_e, #x); } while (0)
+int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
+                   double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st);
+int launch_cost(PgEnv* env, const double* pose, const double* fins, int B, float* latent, float* logit, cudaStream_t st);
+int launch_score(PgEnv* env, const float* pts, const float* df, const uint8_t* mask, const float* grasp, int B, int P,
+                 float* latent, float* logit, cudaStream_t st);
+int launch_accumulate_cost(const float* logit, int K, int N, double* J, cudaStream_t st);
+}

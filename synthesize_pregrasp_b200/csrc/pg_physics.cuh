@@ -1,0 +1,790 @@
+// Batched rigid-body stepping: one rollout per thread, all state in registers / thread-local memory.
+//
+// Replaces, for K rollouts at once, what the reference obtains from one PyBullet world per CPU process:
+//   envs/plate_contact_graph_env.py:176-250 (reset), :454-482 (pre_simulate), :504-533 (servo loop),
+//   :556-603 (settle) -> pybullet.stepSimulation / createConstraint / changeConstraint /
+//   resetBasePositionAndOrientation / setCollisionFilterPair.
+// The stepping scheme is the one the recorded reference trajectories pin (DESIGN.md "Physics"):
+// gravity + proportional damping + gyroscopic term, box-box SAT narrowphase with persistent 4-point
+// manifolds, fixed-iteration projected Gauss-Seidel (fingertip servo rows in alternating order, normal
+// rows, paired cone-friction rows, residual early-out), semi-implicit Euler with exponential-map
+// orientation update, dt = 1/250 s.  fp64 throughout: contact-rich rollouts amplify rounding.
+#pragma once
+#include "pg_env.cuh"
+
+namespace pg {
+
+enum { B_OBJ = MAX_STATICS, B_TIP0 = MAX_STATICS + 1, B_TIP1 = MAX_STATICS + 2, NBODY = MAX_STATICS + 3 };
+enum { MAXM = 12, MAXPTS = 24 };
+
+#define PG_EPS 2.220446049250313e-16
+#define PG_LARGE 1e30
+
+struct DynBody {
+  V3 pos, v, w;
+  Q4 q;
+  M3 R;
+  V3 inertia, half;
+  double mass, friction;
+};
+
+struct MPoint {
+  V3 localA, localB, normalB;
+  double dist;
+};
+
+struct Manifold {
+  MPoint p[4];
+  double breaking;
+  short a, b, n, pad;
+};
+
+struct FixedCons {
+  V3 pivotB;
+  M3 frameB;
+  double max_impulse;
+  int active;
+};
+
+struct Row {          // one scalar constraint row
+  V3 ax;              // linear jacobian of body A (body B gets -ax)
+  V3 tA, tB;          // angular jacobians
+  V3 wA, wB;          // angular unit-impulse responses (I^-1 t, world frame)
+  double rhs, inv, imp;
+};
+
+struct Sim {
+  DynBody dyn[3];     // obj, tip0, tip1
+  Manifold man[MAXM];
+  int nman;
+  FixedCons cons[2];
+  unsigned filter_off;   // bit i: tip i <-> object collision disabled
+  int obj_first;         // reset substep: object proxy is older than the walls'
+  int last_iterations;
+};
+
+// -------------------------------------------------------------------------------------------------
+PG_HD bool is_static(int b) { return b < MAX_STATICS; }
+
+struct BodyView { V3 pos; M3 R; V3 half; double friction; };
+
+PG_HD BodyView view(const EnvDev& E, const Sim& S, const M3* statR, int b) {
+  BodyView v;
+  if (is_static(b)) {
+    const BoxBody& s = E.statics[b];
+    v.pos = V3(s.pos[0], s.pos[1], s.pos[2]);
+    v.R = statR[b];
+    v.half = V3(s.half[0], s.half[1], s.half[2]);
+    v.friction = s.friction;
+  } else {
+    const DynBody& d = S.dyn[b - MAX_STATICS];
+    v.pos = d.pos; v.R = d.R; v.half = d.half; v.friction = d.friction;
+  }
+  return v;
+}
+
+PG_HD void aabb_of(const BodyView& b, double extra, V3& lo, V3& hi) {
+  V3 we;
+  for (int i = 0; i < 3; i++)
+    we[i] = fabs(b.R(i, 0)) * b.half.x + fabs(b.R(i, 1)) * b.half.y + fabs(b.R(i, 2)) * b.half.z;
+  lo = b.pos - we - V3(extra, extra, extra);
+  hi = b.pos + we + V3(extra, extra, extra);
+}
+
+PG_HD bool overlap(V3 alo, V3 ahi, V3 blo, V3 bhi) {
+  for (int k = 0; k < 3; k++) if (alo[k] > bhi[k] || ahi[k] < blo[k]) return false;
+  return true;
+}
+
+// ---------------------------------------------------------------- persistent manifold ---------------
+PG_HD int cache_entry(const Manifold& m, V3 localA) {
+  double shortest = m.breaking * m.breaking;
+  int nearest = -1;
+  for (int i = 0; i < m.n; i++) {
+    V3 d = m.p[i].localA - localA;
+    double dd = dot(d, d);
+    if (dd < shortest) { shortest = dd; nearest = i; }
+  }
+  return nearest;
+}
+
+PG_HD int sort_cached(const Manifold& m, V3 localA, double dist) {
+  int maxPenIdx = -1;
+  double maxPen = dist;
+  for (int i = 0; i < 4; i++) if (m.p[i].dist < maxPen) { maxPenIdx = i; maxPen = m.p[i].dist; }
+  double res[4] = {0, 0, 0, 0};
+  if (maxPenIdx != 0) { V3 c = cross(localA - m.p[1].localA, m.p[3].localA - m.p[2].localA); res[0] = dot(c, c); }
+  if (maxPenIdx != 1) { V3 c = cross(localA - m.p[0].localA, m.p[3].localA - m.p[2].localA); res[1] = dot(c, c); }
+  if (maxPenIdx != 2) { V3 c = cross(localA - m.p[0].localA, m.p[3].localA - m.p[1].localA); res[2] = dot(c, c); }
+  if (maxPenIdx != 3) { V3 c = cross(localA - m.p[0].localA, m.p[2].localA - m.p[1].localA); res[3] = dot(c, c); }
+  int best = -1; double bv = -PG_LARGE;
+  for (int i = 0; i < 4; i++) if (fabs(res[i]) > bv) { best = i; bv = fabs(res[i]); }
+  return best;
+}
+
+struct Sink { Manifold* m; V3 posA, posB; M3 RA, RB; };
+
+PG_HD void add_contact(Sink& s, V3 normalOnB, V3 pointOnB, double depth) {
+  Manifold& m = *s.m;
+  if (depth > m.breaking) return;
+  V3 pointA = pointOnB + normalOnB * depth;
+  MPoint np;
+  np.localA = mulT(s.RA, pointA - s.posA);
+  np.localB = mulT(s.RB, pointOnB - s.posB);
+  np.normalB = normalOnB; np.dist = depth;
+  int idx = cache_entry(m, np.localA);
+  if (idx < 0) {
+    idx = m.n;
+    if (idx == 4) idx = sort_cached(m, np.localA, depth); else m.n++;
+    if (idx < 0) idx = 0;
+  }
+  m.p[idx] = np;
+}
+
+PG_HD void refresh(Manifold& m, const BodyView& A, const BodyView& B) {
+  V3 pa[4], pb[4];
+  for (int i = m.n - 1; i >= 0; i--) {
+    pa[i] = mul(A.R, m.p[i].localA) + A.pos;
+    pb[i] = mul(B.R, m.p[i].localB) + B.pos;
+    m.p[i].dist = dot(pa[i] - pb[i], m.p[i].normalB);
+  }
+  for (int i = m.n - 1; i >= 0; i--) {
+    bool rm = false;
+    if (!(m.p[i].dist <= m.breaking)) rm = true;
+    else {
+      V3 proj = pa[i] - m.p[i].normalB * m.p[i].dist;
+      V3 d = pb[i] - proj;
+      if (dot(d, d) > m.breaking * m.breaking) rm = true;
+    }
+    if (rm) {
+      int last = m.n - 1;
+      if (i != last) { m.p[i] = m.p[last]; pa[i] = pa[last]; pb[i] = pb[last]; }
+      m.n--;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- box-box narrowphase ----------------
+PG_HD void line_closest(V3 pa, V3 ua, V3 pb, V3 ub, double* alpha, double* beta) {
+  V3 p = pb - pa;
+  double uaub = dot(ua, ub), q1 = dot(ua, p), q2 = -dot(ub, p);
+  double d = 1 - uaub * uaub;
+  if (d <= (double)0.0001f) { *alpha = 0; *beta = 0; }
+  else { d = 1.0 / d; *alpha = (q1 + uaub * q2) * d; *beta = (uaub * q1 + q2) * d; }
+}
+
+PG_HDN int rect_quad(const double h[2], const double p[8], double ret[16]) {
+  int nq = 4, nr = 0;
+  double bufA[16], bufB[16];
+  for (int i = 0; i < 8; i++) bufA[i] = p[i];
+  double* q = bufA;
+  double* r = bufB;
+  for (int dir = 0; dir <= 1; dir++) {
+    for (int sign = -1; sign <= 1; sign += 2) {
+      const double* pq = q;
+      double* pr = r;
+      nr = 0;
+      bool full = false;
+      for (int i = nq; i > 0 && !full; i--) {
+        if (sign * pq[dir] < h[dir]) {
+          pr[0] = pq[0]; pr[1] = pq[1]; pr += 2; nr++;
+          if (nr & 8) { full = true; break; }
+        }
+        const double* nextq = (i > 1) ? pq + 2 : q;
+        if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
+          pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
+          pr[dir] = sign * h[dir];
+          pr += 2; nr++;
+          if (nr & 8) { full = true; break; }
+        }
+        pq += 2;
+      }
+      double* t = q; q = r; r = t;
+      if (full) { dir = 2; break; }
+      nq = nr;
+    }
+  }
+  for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
+  return nr;
+}
+
+PG_HDN void cull_points(int n, const double p[], int m, int i0, int iret[]) {
+  const double MPI = (double)3.14159265f;
+  double a, cx, cy, q;
+  if (n == 1) { cx = p[0]; cy = p[1]; }
+  else if (n == 2) { cx = 0.5 * (p[0] + p[2]); cy = 0.5 * (p[1] + p[3]); }
+  else {
+    a = 0; cx = 0; cy = 0;
+    for (int i = 0; i < (n - 1); i++) {
+      q = p[i * 2] * p[i * 2 + 3] - p[i * 2 + 2] * p[i * 2 + 1];
+      a += q;
+      cx += q * (p[i * 2] + p[i * 2 + 2]);
+      cy += q * (p[i * 2 + 1] + p[i * 2 + 3]);
+    }
+    q = p[n * 2 - 2] * p[1] - p[0] * p[n * 2 - 1];
+    if (fabs(a + q) > PG_EPS) a = 1.0 / (3.0 * (a + q)); else a = PG_LARGE;
+    cx = a * (cx + q * (p[n * 2 - 2] + p[0]));
+    cy = a * (cy + q * (p[n * 2 - 1] + p[1]));
+  }
+  double A[8];
+  int avail[8];
+  for (int i = 0; i < n; i++) { A[i] = atan2(p[i * 2 + 1] - cy, p[i * 2] - cx); avail[i] = 1; }
+  avail[i0] = 0;
+  iret[0] = i0;
+  int k = 1;
+  for (int j = 1; j < m; j++) {
+    a = double(j) * (2 * MPI / m) + A[i0];
+    if (a > MPI) a -= 2 * MPI;
+    double maxdiff = 1e9, diff;
+    iret[k] = i0;
+    for (int i = 0; i < n; i++) {
+      if (avail[i]) {
+        diff = fabs(A[i] - a);
+        if (diff > MPI) diff = 2 * MPI - diff;
+        if (diff < maxdiff) { maxdiff = diff; iret[k] = i; }
+      }
+    }
+    avail[iret[k]] = 0;
+    k++;
+  }
+}
+
+// btBoxBoxDetector (ODE dBoxBox2).  Box 1 = manifold body A, box 2 = body B.
+PG_HDN void box_box(const BodyView& b1, const BodyView& b2, Sink& out) {
+  const double fudge_factor = 1.05;
+  const M3& R1 = b1.R;
+  const M3& R2 = b2.R;
+  V3 p = b2.pos - b1.pos, pp = mulT(R1, p), normalC;
+  double A[3], B[3], R[3][3], Q[3][3], s, s2, l;
+  int nbox = 0, ncol = -1, invert_normal = 0, code = 0;
+  for (int i = 0; i < 3; i++) { A[i] = (2.0 * b1.half[i]) * 0.5; B[i] = (2.0 * b2.half[i]) * 0.5; }
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { R[i][j] = dot(R1.col(i), R2.col(j)); Q[i][j] = fabs(R[i][j]); }
+  s = -INFINITY;
+#define PG_TST1(expr1, expr2, box, col, cc) \
+  { double e1 = (expr1); s2 = fabs(e1) - (expr2); if (s2 > 0) return; \
+    if (s2 > s) { s = s2; nbox = box; ncol = col; invert_normal = (e1 < 0); code = (cc); } }
+  PG_TST1(pp[0], (A[0] + B[0] * Q[0][0] + B[1] * Q[0][1] + B[2] * Q[0][2]), 1, 0, 1);
+  PG_TST1(pp[1], (A[1] + B[0] * Q[1][0] + B[1] * Q[1][1] + B[2] * Q[1][2]), 1, 1, 2);
+  PG_TST1(pp[2], (A[2] + B[0] * Q[2][0] + B[1] * Q[2][1] + B[2] * Q[2][2]), 1, 2, 3);
+  PG_TST1(dot(R2.col(0), p), (A[0] * Q[0][0] + A[1] * Q[1][0] + A[2] * Q[2][0] + B[0]), 2, 0, 4);
+  PG_TST1(dot(R2.col(1), p), (A[0] * Q[0][1] + A[1] * Q[1][1] + A[2] * Q[2][1] + B[1]), 2, 1, 5);
+  PG_TST1(dot(R2.col(2), p), (A[0] * Q[0][2] + A[1] * Q[1][2] + A[2] * Q[2][2] + B[2]), 2, 2, 6);
+#undef PG_TST1
+#define PG_TST2(expr1, expr2, n1, n2, n3, cc) \
+  { double e1 = (expr1); s2 = fabs(e1) - (expr2); if (s2 > PG_EPS) return; \
+    l = sqrt((n1) * (n1) + (n2) * (n2) + (n3) * (n3)); \
+    if (l > PG_EPS) { s2 /= l; if (s2 * fudge_factor > s) { s = s2; ncol = -1; \
+      normalC = V3((n1) / l, (n2) / l, (n3) / l); invert_normal = (e1 < 0); code = (cc); } } }
+  const double fudge2 = (double)1.0e-5f;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Q[i][j] += fudge2;
+  PG_TST2(pp[2] * R[1][0] - pp[1] * R[2][0], (A[1] * Q[2][0] + A[2] * Q[1][0] + B[1] * Q[0][2] + B[2] * Q[0][1]), 0, -R[2][0], R[1][0], 7);
+  PG_TST2(pp[2] * R[1][1] - pp[1] * R[2][1], (A[1] * Q[2][1] + A[2] * Q[1][1] + B[0] * Q[0][2] + B[2] * Q[0][0]), 0, -R[2][1], R[1][1], 8);
+  PG_TST2(pp[2] * R[1][2] - pp[1] * R[2][2], (A[1] * Q[2][2] + A[2] * Q[1][2] + B[0] * Q[0][1] + B[1] * Q[0][0]), 0, -R[2][2], R[1][2], 9);
+  PG_TST2(pp[0] * R[2][0] - pp[2] * R[0][0], (A[0] * Q[2][0] + A[2] * Q[0][0] + B[1] * Q[1][2] + B[2] * Q[1][1]), R[2][0], 0, -R[0][0], 10);
+  PG_TST2(pp[0] * R[2][1] - pp[2] * R[0][1], (A[0] * Q[2][1] + A[2] * Q[0][1] + B[0] * Q[1][2] + B[2] * Q[1][0]), R[2][1], 0, -R[0][1], 11);
+  PG_TST2(pp[0] * R[2][2] - pp[2] * R[0][2], (A[0] * Q[2][2] + A[2] * Q[0][2] + B[0] * Q[1][1] + B[1] * Q[1][0]), R[2][2], 0, -R[0][2], 12);
+  PG_TST2(pp[1] * R[0][0] - pp[0] * R[1][0], (A[0] * Q[1][0] + A[1] * Q[0][0] + B[1] * Q[2][2] + B[2] * Q[2][1]), -R[1][0], R[0][0], 0, 13);
+  PG_TST2(pp[1] * R[0][1] - pp[0] * R[1][1], (A[0] * Q[1][1] + A[1] * Q[0][1] + B[0] * Q[2][2] + B[2] * Q[2][0]), -R[1][1], R[0][1], 0, 14);
+  PG_TST2(pp[1] * R[0][2] - pp[0] * R[1][2], (A[0] * Q[1][2] + A[1] * Q[0][2] + B[0] * Q[2][1] + B[1] * Q[2][0]), -R[1][2], R[0][2], 0, 15);
+#undef PG_TST2
+  if (!code) return;
+  V3 normal;
+  if (ncol >= 0) normal = (nbox == 1 ? R1 : R2).col(ncol);
+  else normal = mul(R1, normalC);
+  if (invert_normal) normal = -normal;
+  double depth = -s;
+
+  if (code > 6) {
+    V3 pa = b1.pos;
+    for (int j = 0; j < 3; j++) {
+      double sign = (dot(normal, R1.col(j)) > 0) ? 1.0 : -1.0;
+      pa += R1.col(j) * (sign * A[j]);
+    }
+    V3 pb = b2.pos;
+    for (int j = 0; j < 3; j++) {
+      double sign = (dot(normal, R2.col(j)) > 0) ? -1.0 : 1.0;
+      pb += R2.col(j) * (sign * B[j]);
+    }
+    double alpha, beta;
+    V3 ua = R1.col((code - 7) / 3), ub = R2.col((code - 7) % 3);
+    line_closest(pa, ua, pb, ub, &alpha, &beta);
+    pb += ub * beta;
+    add_contact(out, -normal, pb, -depth);
+    return;
+  }
+
+  const M3& Ra = (code <= 3) ? R1 : R2;
+  const M3& Rb = (code <= 3) ? R2 : R1;
+  V3 pa = (code <= 3) ? b1.pos : b2.pos, pb = (code <= 3) ? b2.pos : b1.pos;
+  const double* Sa = (code <= 3) ? A : B;
+  const double* Sb = (code <= 3) ? B : A;
+  V3 normal2 = (code <= 3) ? normal : -normal;
+  V3 nr = mulT(Rb, normal2), anr(fabs(nr.x), fabs(nr.y), fabs(nr.z));
+  int lanr, a1, a2;
+  if (anr[1] > anr[0]) {
+    if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
+  } else {
+    if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; } else { a1 = 0; a2 = 1; lanr = 2; }
+  }
+  V3 center;
+  if (nr[lanr] < 0) center = pb - pa + Rb.col(lanr) * Sb[lanr];
+  else center = pb - pa - Rb.col(lanr) * Sb[lanr];
+  int codeN = (code <= 3) ? code - 1 : code - 4, code1, code2;
+  if (codeN == 0) { code1 = 1; code2 = 2; } else if (codeN == 1) { code1 = 0; code2 = 2; } else { code1 = 0; code2 = 1; }
+  double quad[8], c1, c2, m11, m12, m21, m22;
+  c1 = dot(center, Ra.col(code1));
+  c2 = dot(center, Ra.col(code2));
+  m11 = dot(Ra.col(code1), Rb.col(a1));
+  m12 = dot(Ra.col(code1), Rb.col(a2));
+  m21 = dot(Ra.col(code2), Rb.col(a1));
+  m22 = dot(Ra.col(code2), Rb.col(a2));
+  {
+    double k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
+    quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4;
+    quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
+    quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4;
+    quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
+  }
+  double rect[2] = {Sa[code1], Sa[code2]};
+  double ret[16];
+  int n = rect_quad(rect, quad, ret);
+  if (n < 1) return;
+  V3 point[8];
+  double dep[8];
+  double det1 = 1.0 / (m11 * m22 - m12 * m21);
+  m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
+  int cnum = 0;
+  for (int j = 0; j < n; j++) {
+    double k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
+    double k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
+    point[cnum] = center + Rb.col(a1) * k1 + Rb.col(a2) * k2;
+    dep[cnum] = Sa[codeN] - dot(normal2, point[cnum]);
+    if (dep[cnum] >= 0) { ret[cnum * 2] = ret[j * 2]; ret[cnum * 2 + 1] = ret[j * 2 + 1]; cnum++; }
+  }
+  if (cnum < 1) return;
+  int maxc = 4;
+  if (maxc > cnum) maxc = cnum;
+  if (cnum <= maxc) {
+    for (int j = 0; j < cnum; j++) {
+      V3 pw = point[j] + pa;
+      if (code >= 4) pw = pw - normal * dep[j];
+      add_contact(out, -normal, pw, -dep[j]);
+    }
+  } else {
+    int i1 = 0;
+    double maxdepth = dep[0];
+    for (int i = 1; i < cnum; i++) if (dep[i] > maxdepth) { maxdepth = dep[i]; i1 = i; }
+    int iret[8];
+    cull_points(cnum, ret, maxc, i1, iret);
+    for (int j = 0; j < maxc; j++) {
+      V3 pw = point[iret[j]] + pa;
+      if (code >= 4) pw = pw - normal * dep[iret[j]];
+      add_contact(out, -normal, pw, -dep[iret[j]]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- collision pipeline -----------------
+PG_HD double bs_radius(const EnvDev& E, int b) {
+  if (is_static(b)) return E.static_radius_bs[b];
+  if (b == B_OBJ) return E.obj_radius_bs;
+  return E.tip_radius_bs[b - B_TIP0];
+}
+
+PG_HD bool pair_allowed(const EnvDev& E, const Sim& S, int i, int j) {   // i < j in body-id order
+  if (is_static(i) && is_static(j)) return false;
+  if (is_static(i) && i >= E.n_static) return false;
+  // tip <-> floor collisions are disabled at reset (plate_env:228)
+  if (i == E.floor_index && (j == B_TIP0 || j == B_TIP1)) return false;
+  if (i == B_OBJ && j >= B_TIP0 && ((S.filter_off >> (j - B_TIP0)) & 1u)) return false;
+  return true;
+}
+
+PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
+  BodyView bv[NBODY];
+  V3 lo[NBODY], hi[NBODY];
+  for (int d = 0; d < 3; d++) S.dyn[d].R = qmat(S.dyn[d].q);
+  for (int b = 0; b < NBODY; b++) {
+    if (is_static(b) && b >= E.n_static) continue;
+    bv[b] = view(E, S, statR, b);
+    aabb_of(bv[b], E.aabb_margin, lo[b], hi[b]);
+  }
+  auto pair_overlap = [&](int a, int b) -> bool {
+    if (!overlap(lo[a], hi[a], lo[b], hi[b])) return false;
+    bool comp = (is_static(a) && E.statics[a].compound) || (is_static(b) && E.statics[b].compound);
+    if (comp) {   // btCompoundCollisionAlgorithm: child manifold lives only while the TIGHT aabbs overlap
+      double e = E.aabb_margin;
+      for (int k = 0; k < 3; k++)
+        if (lo[a][k] + e > hi[b][k] - e || hi[a][k] - e < lo[b][k] + e) return false;
+    }
+    return true;
+  };
+  // drop manifolds whose pair separated (dispatcher swap-remove)
+  for (int i = 0; i < S.nman;) {
+    Manifold& m = S.man[i];
+    if (!pair_overlap(m.a, m.b)) { if (i != S.nman - 1) S.man[i] = S.man[S.nman - 1]; S.nman--; }
+    else i++;
+  }
+  // new manifolds in the order the broadphase reports the object's pairs: thumb, floor, index tip, walls,
+  // then wall-tip pairs and tip-tip (DESIGN.md "Row order")
+  int ca[MAXM + 4], cb[MAXM + 4], nc = 0;
+  ca[nc] = B_OBJ; cb[nc++] = B_TIP0;
+  ca[nc] = E.floor_index; cb[nc++] = B_OBJ;
+  ca[nc] = B_OBJ; cb[nc++] = B_TIP1;
+  for (int s = 0; s < E.n_static; s++) if (s != E.floor_index) { ca[nc] = s; cb[nc++] = B_OBJ; }
+  for (int s = 0; s < E.n_static; s++) if (s != E.floor_index) { ca[nc] = s; cb[nc++] = B_TIP0; ca[nc] = s; cb[nc++] = B_TIP1; }
+  ca[nc] = B_TIP0; cb[nc++] = B_TIP1;
+  for (int c = 0; c < nc; c++) {
+    int i = ca[c] < cb[c] ? ca[c] : cb[c], j = ca[c] < cb[c] ? cb[c] : ca[c];
+    if (!pair_allowed(E, S, i, j)) continue;
+    if (!pair_overlap(i, j)) continue;
+    bool have = false;
+    for (int k = 0; k < S.nman; k++) if ((S.man[k].a == i && S.man[k].b == j) || (S.man[k].a == j && S.man[k].b == i)) have = true;
+    if (have || S.nman >= MAXM) continue;
+    Manifold& m = S.man[S.nman++];
+    m.n = 0;
+    // body A: the compound floor always; otherwise the older broadphase proxy.  After the first
+    // pre_simulate the object's proxy is the youngest, so it is body B of every pair.
+    if (is_static(i) && !E.statics[i].compound && j == B_OBJ && S.obj_first) { m.a = (short)j; m.b = (short)i; }
+    else { m.a = (short)i; m.b = (short)j; }
+    if (i == B_OBJ) { m.a = (short)j; m.b = (short)i; }      // (tip, obj): tip proxy is older
+    double ta = bs_radius(E, m.a) * E.breaking_factor, tb = bs_radius(E, m.b) * E.breaking_factor;
+    m.breaking = ta < tb ? ta : tb;
+  }
+  for (int k = 0; k < S.nman; k++) {
+    Manifold& m = S.man[k];
+    Sink sink;
+    sink.m = &m; sink.posA = bv[m.a].pos; sink.posB = bv[m.b].pos; sink.RA = bv[m.a].R; sink.RB = bv[m.b].R;
+    box_box(bv[m.a], bv[m.b], sink);
+    refresh(m, bv[m.a], bv[m.b]);
+  }
+}
+
+// ---------------------------------------------------------------- dynamics ---------------------------
+PG_HD void apply_external(const EnvDev& E, Sim& S) {
+  for (int d = 0; d < 3; d++) {
+    DynBody& b = S.dyn[d];
+    V3 wl = mulT(b.R, b.w), vl = mulT(b.R, b.v);
+    V3 force_l = mulT(b.R, V3(0, 0, E.gravity_z * b.mass));
+    V3 zero_ang, zero_lin = -force_l;
+    double wn = len(wl), vn = len(vl);
+    zero_ang += mulc(b.inertia, wl) * (E.ang_damping + E.ang_damping * wn);
+    zero_lin += vl * (b.mass * (E.lin_damping + E.lin_damping * vn));
+    zero_ang += cross(wl, mulc(b.inertia, wl));
+    zero_lin += cross(wl, vl) * b.mass;
+    V3 acc_ang(-zero_ang.x / b.inertia.x, -zero_ang.y / b.inertia.y, -zero_ang.z / b.inertia.z);
+    V3 acc_lin(-zero_lin.x / b.mass, -zero_lin.y / b.mass, -zero_lin.z / b.mass);
+    V3 wdot = mul(b.R, acc_ang);
+    V3 vdot = mul(b.R, acc_lin + cross(wl, vl));
+    for (int k = 0; k < 3; k++) {
+      b.w[k] += wdot[k] * E.dt; b.w[k] = fmax(-E.max_coord_vel, fmin(E.max_coord_vel, b.w[k]));
+    }
+    for (int k = 0; k < 3; k++) {
+      b.v[k] += vdot[k] * E.dt; b.v[k] = fmax(-E.max_coord_vel, fmin(E.max_coord_vel, b.v[k]));
+    }
+  }
+}
+
+PG_HD V3 ang_response(const DynBody& b, V3 t) {
+  V3 tl = mulT(b.R, t);
+  V3 al(tl.x / b.inertia.x, tl.y / b.inertia.y, tl.z / b.inertia.z);
+  return mul(b.R, al);
+}
+
+struct DV { V3 w, v; };   // accumulated delta velocity of one dynamic body
+
+PG_HD double jdot(V3 t, V3 ax, const DV& d) {
+  double s = 0;
+  s += t.x * d.w.x; s += t.y * d.w.y; s += t.z * d.w.z;
+  s += ax.x * d.v.x; s += ax.y * d.v.y; s += ax.z * d.v.z;
+  return s;
+}
+
+struct RowSet {
+  Row nc[12];
+  Row normal[MAXPTS];
+  Row fric[2 * MAXPTS];
+  short nA[MAXPTS], nB[MAXPTS];   // body ids per contact point
+  double mu[MAXPTS];
+  int n_nc, n_pts;
+  short nc_body[12];
+};
+
+PG_HD void setup_contact_row(const EnvDev& E, const Sim& S, Row& r, int bA, int bB, V3 relA, V3 relB, V3 axis,
+                             double dist, bool is_friction) {
+  r.ax = axis;
+  r.tA = cross(relA, axis);
+  r.tB = cross(relB, -axis);
+  double denom0 = 0, denom1 = 0, rel_vel = 0;
+  if (!is_static(bA)) {
+    const DynBody& A = S.dyn[bA - MAX_STATICS];
+    r.wA = ang_response(A, r.tA);
+    V3 lin = axis / A.mass;
+    denom0 += r.tA.x * r.wA.x; denom0 += r.tA.y * r.wA.y; denom0 += r.tA.z * r.wA.z;
+    denom0 += axis.x * lin.x; denom0 += axis.y * lin.y; denom0 += axis.z * lin.z;
+    double s = 0;
+    s += A.w.x * r.tA.x; s += A.w.y * r.tA.y; s += A.w.z * r.tA.z;
+    s += A.v.x * axis.x; s += A.v.y * axis.y; s += A.v.z * axis.z;
+    rel_vel += s;
+  } else r.wA = V3();
+  if (!is_static(bB)) {
+    const DynBody& B = S.dyn[bB - MAX_STATICS];
+    V3 nax = -axis;
+    r.wB = ang_response(B, r.tB);
+    V3 lin = nax / B.mass;
+    denom1 += r.tB.x * r.wB.x; denom1 += r.tB.y * r.wB.y; denom1 += r.tB.z * r.wB.z;
+    denom1 += nax.x * lin.x; denom1 += nax.y * lin.y; denom1 += nax.z * lin.z;
+    double s = 0;
+    s += B.w.x * r.tB.x; s += B.w.y * r.tB.y; s += B.w.z * r.tB.z;
+    s += B.v.x * nax.x; s += B.v.y * nax.y; s += B.v.z * nax.z;
+    rel_vel += s;
+  } else r.wB = V3();
+  double d = denom0 + denom1;
+  r.inv = (d > PG_EPS) ? 1.0 / d : 0.0;
+  double distance = is_friction ? 0.0 : dist + E.slop;
+  double positionalError = 0, velocityError = 0 - rel_vel;
+  if (is_friction) positionalError = -distance * E.erp2 / E.dt;
+  else {
+    if (distance > 0) { positionalError = 0; velocityError -= distance / E.dt; }
+    else positionalError = -distance * E.erp2 / E.dt;
+  }
+  r.rhs = positionalError * r.inv + velocityError * r.inv;
+  r.imp = 0;
+}
+
+PG_HD void matrix_to_euler_xyz(const M3& mat, V3& xyz) {
+  // element(idx) = mat[idx % 3][idx / 3]
+#define PG_EL(idx) mat((idx) % 3, (idx) / 3)
+  double fi = PG_EL(2);
+  if (fi < 1.0) {
+    if (fi > -1.0) { xyz.x = atan2(-PG_EL(5), PG_EL(8)); xyz.y = asin(PG_EL(2)); xyz.z = atan2(-PG_EL(1), PG_EL(0)); }
+    else { xyz.x = -atan2(PG_EL(3), PG_EL(4)); xyz.y = -1.57079632679489661923; xyz.z = 0; }
+  } else { xyz.x = atan2(PG_EL(3), PG_EL(4)); xyz.y = 1.57079632679489661923; xyz.z = 0; }
+#undef PG_EL
+}
+
+PG_HD void setup_fixed_rows(const EnvDev& E, const Sim& S, int slot, RowSet& rs) {
+  const FixedCons& c = S.cons[slot];
+  const DynBody& A = S.dyn[1 + slot];
+  M3 relRot;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) relRot(i, j) = dot(A.R.col(i), c.frameB.col(j));
+  V3 angleDiff;
+  matrix_to_euler_xyz(relRot, angleDiff);
+  for (int i = 0; i < 6; i++) {
+    Row& r = rs.nc[rs.n_nc];
+    rs.nc_body[rs.n_nc] = (short)(B_TIP0 + slot);
+    rs.n_nc++;
+    V3 nl, na;
+    double posError;
+    if (i < 3) { nl[i] = 1; posError = dot(A.pos - c.pivotB, nl); }
+    else { na = A.R.col(i % 3); posError = angleDiff[i % 3]; }
+    V3 oc = cross(V3(), nl);           // pivot coincides with the tip's centre of mass
+    r.tA = oc + na; r.ax = nl; r.tB = V3(); r.wB = V3();
+    r.wA = ang_response(A, r.tA);
+    V3 lin = nl / A.mass;
+    double d = 0;
+    d += r.tA.x * r.wA.x; d += r.tA.y * r.wA.y; d += r.tA.z * r.wA.z;
+    d += nl.x * lin.x; d += nl.y * lin.y; d += nl.z * lin.z;
+    r.inv = (d > PG_EPS) ? 1.0 / d : 0.0;
+    double rel_vel = 0;
+    rel_vel += A.w.x * r.tA.x; rel_vel += A.w.y * r.tA.y; rel_vel += A.w.z * r.tA.z;
+    rel_vel += A.v.x * nl.x; rel_vel += A.v.y * nl.y; rel_vel += A.v.z * nl.z;
+    double velocityError = (0 - rel_vel) * 1.0;
+    double positionalError = -posError * E.erp / E.dt;
+    r.rhs = positionalError * r.inv + velocityError * r.inv;
+    r.imp = 0;
+  }
+}
+
+// delta impulse of a row against the current delta-velocities
+PG_HD double row_delta(const Row& r, int bA, int bB, const DV* dv) {
+  double delta = r.rhs;   // cfm = 0
+  double a = 0, b = 0;
+  if (bA >= MAX_STATICS) a = jdot(r.tA, r.ax, dv[bA - MAX_STATICS]);
+  if (bB >= MAX_STATICS) b = jdot(r.tB, -r.ax, dv[bB - MAX_STATICS]);
+  delta -= a * r.inv;
+  delta -= b * r.inv;
+  return delta;
+}
+
+PG_HD void row_apply(const Sim& S, const Row& r, int bA, int bB, DV* dv, double dimp) {
+  if (bA >= MAX_STATICS) {
+    DV& d = dv[bA - MAX_STATICS];
+    double im = S.dyn[bA - MAX_STATICS].mass;
+    d.w.x += r.wA.x * dimp; d.w.y += r.wA.y * dimp; d.w.z += r.wA.z * dimp;
+    d.v.x += (r.ax.x / im) * dimp; d.v.y += (r.ax.y / im) * dimp; d.v.z += (r.ax.z / im) * dimp;
+  }
+  if (bB >= MAX_STATICS) {
+    DV& d = dv[bB - MAX_STATICS];
+    double im = S.dyn[bB - MAX_STATICS].mass;
+    d.w.x += r.wB.x * dimp; d.w.y += r.wB.y * dimp; d.w.z += r.wB.z * dimp;
+    d.v.x += (-r.ax.x / im) * dimp; d.v.y += (-r.ax.y / im) * dimp; d.v.z += (-r.ax.z / im) * dimp;
+  }
+}
+
+PG_HD double resolve_row(const Sim& S, Row& r, int bA, int bB, DV* dv, double lo, double hi) {
+  double delta = row_delta(r, bA, bB, dv);
+  double sum = r.imp + delta;
+  if (sum < lo) { delta = lo - r.imp; r.imp = lo; }
+  else if (sum > hi) { delta = hi - r.imp; r.imp = hi; }
+  else r.imp = sum;
+  row_apply(S, r, bA, bB, dv, delta);
+  return delta / r.inv;
+}
+
+// btAlignedObjectArray::quickSortInternal on (key, payload) pairs, explicit stack
+PG_HD void bt_quicksort(int* key, int* val, int n) {
+  if (n < 2) return;
+  int stack_lo[16], stack_hi[16], sp = 0;
+  stack_lo[0] = 0; stack_hi[0] = n - 1; sp = 1;
+  while (sp > 0) {
+    sp--;
+    int lo = stack_lo[sp], hi = stack_hi[sp];
+    int i = lo, j = hi, x = key[(lo + hi) / 2];
+    do {
+      while (key[i] < x) i++;
+      while (x < key[j]) j--;
+      if (i <= j) { int t = key[i]; key[i] = key[j]; key[j] = t; t = val[i]; val[i] = val[j]; val[j] = t; i++; j--; }
+    } while (i <= j);
+    // the recursion order of the original (left first) does not change the result: the halves are disjoint
+    if (i < hi) { stack_lo[sp] = i; stack_hi[sp] = hi; sp++; }
+    if (lo < j) { stack_lo[sp] = lo; stack_hi[sp] = j; sp++; }
+  }
+}
+
+PG_HDN void solve(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs) {
+  // islands over the (overlapping-pair) manifolds; tags: obj 0, tip0 1, tip1 2
+  int uf[3] = {0, 1, 2};
+  for (int k = 0; k < S.nman; k++) {
+    int a = S.man[k].a, b = S.man[k].b;
+    if (a >= MAX_STATICS && b >= MAX_STATICS) {
+      int i = a - MAX_STATICS, j = b - MAX_STATICS;
+      while (uf[i] != i) i = uf[i];
+      while (uf[j] != j) j = uf[j];
+      if (i != j) uf[i] = j;
+    }
+  }
+  int tag[3];
+  for (int d = 0; d < 3; d++) { int i = d; while (uf[i] != i) i = uf[i]; tag[d] = i; }
+  int mkey[MAXM], mval[MAXM];
+  for (int k = 0; k < S.nman; k++) {
+    int a = S.man[k].a, b = S.man[k].b;
+    mkey[k] = (a >= MAX_STATICS) ? tag[a - MAX_STATICS] : tag[b - MAX_STATICS];
+    mval[k] = k;
+  }
+  bt_quicksort(mkey, mval, S.nman);
+  int ckey[2], cval[2], ncons = 0;
+  for (int c = 0; c < 2; c++) if (S.cons[c].active) { ckey[ncons] = tag[1 + c]; cval[ncons] = c; ncons++; }
+  bt_quicksort(ckey, cval, ncons);
+
+  rs.n_nc = 0; rs.n_pts = 0;
+  for (int o = 0; o < S.nman; o++) {
+    const Manifold& m = S.man[mval[o]];
+    BodyView A = view(E, S, statR, m.a), B = view(E, S, statR, m.b);
+    double f = A.friction * B.friction;
+    if (f < -10.0) f = -10.0;
+    if (f > 10.0) f = 10.0;
+    for (int k = 0; k < m.n && rs.n_pts < MAXPTS; k++) {
+      const MPoint& cp = m.p[k];
+      V3 posA = mul(A.R, cp.localA) + A.pos, posB = mul(B.R, cp.localB) + B.pos;
+      V3 relA = posA - A.pos, relB = posB - B.pos;
+      int idx = rs.n_pts++;
+      rs.nA[idx] = m.a; rs.nB[idx] = m.b; rs.mu[idx] = f;
+      setup_contact_row(E, S, rs.normal[idx], m.a, m.b, relA, relB, cp.normalB, cp.dist, false);
+      V3 l1, l2;
+      plane_space1(cp.normalB, l1, l2);
+      l1 = l1 / len(l1);
+      l2 = l2 / len(l2);
+      setup_contact_row(E, S, rs.fric[2 * idx], m.a, m.b, relA, relB, l1, 0.0, true);
+      setup_contact_row(E, S, rs.fric[2 * idx + 1], m.a, m.b, relA, relB, l2, 0.0, true);
+    }
+  }
+  for (int c = 0; c < ncons; c++) setup_fixed_rows(E, S, cval[c], rs);
+  S.last_iterations = 0;
+  if (rs.n_nc == 0 && rs.n_pts == 0) return;
+
+  DV dv[3];
+  int it;
+  for (it = 0; it < E.iterations; it++) {
+    double lsr = 0;
+    int nn = rs.n_nc;
+    for (int j = 0; j < nn; j++) {
+      int index = (it & 1) ? j : nn - 1 - j;
+      int body = rs.nc_body[index];
+      double mi = S.cons[body - B_TIP0].max_impulse;
+      double res = resolve_row(S, rs.nc[index], body, -1, dv, -mi, mi);
+      lsr = fmax(lsr, res * res);
+    }
+    for (int k = 0; k < rs.n_pts; k++) {
+      double res = resolve_row(S, rs.normal[k], rs.nA[k], rs.nB[k], dv, 0.0, 1e10);
+      lsr = fmax(lsr, res * res);
+    }
+    for (int k = 0; k < rs.n_pts; k++) {
+      Row& cA = rs.fric[2 * k];
+      Row& cB = rs.fric[2 * k + 1];
+      int bA = rs.nA[k], bB = rs.nB[k];
+      double lim = rs.mu[k] * rs.normal[k].imp;
+      double loA = -lim, loB = -lim;
+      double dB = row_delta(cB, bA, bB, dv), sumB = cB.imp + dB;
+      double dA = row_delta(cA, bA, bB, dv), sumA = cA.imp + dA;
+      if (sumA * sumA + sumB * sumB >= loA * loB) {
+        double angle = atan2(sumA, sumB);
+        double ca = fabs(loA * sin(angle)), cb = fabs(loB * cos(angle));
+        if (sumA < -ca) { dA = -ca - cA.imp; cA.imp = -ca; }
+        else if (sumA > ca) { dA = ca - cA.imp; cA.imp = ca; }
+        else cA.imp = sumA;
+        if (sumB < -cb) { dB = -cb - cB.imp; cB.imp = -cb; }
+        else if (sumB > cb) { dB = cb - cB.imp; cB.imp = cb; }
+        else cB.imp = sumB;
+      } else { cA.imp = sumA; cB.imp = sumB; }
+      row_apply(S, cA, bA, bB, dv, dA);
+      row_apply(S, cB, bA, bB, dv, dB);
+      double res = dA / cA.inv + dB / cB.inv;
+      lsr = fmax(lsr, res * res);
+    }
+    if (lsr <= E.residual_threshold || it >= E.iterations - 1) { it++; break; }
+  }
+  S.last_iterations = it;
+  for (int d = 0; d < 3; d++) {
+    DynBody& b = S.dyn[d];
+    b.w.x += dv[d].w.x; b.w.y += dv[d].w.y; b.w.z += dv[d].w.z;
+    b.v.x += dv[d].v.x; b.v.y += dv[d].v.y; b.v.z += dv[d].v.z;
+  }
+}
+
+PG_HD void integrate(const EnvDev& E, Sim& S) {
+  for (int d = 0; d < 3; d++) {
+    DynBody& b = S.dyn[d];
+    b.pos += b.v * E.dt;
+    V3 angvel = b.w;
+    double fAngle = len(angvel);
+    const double THRESH = 0.5 * 1.57079632679489661923;
+    if (fAngle * E.dt > THRESH) fAngle = 0.5 * 1.57079632679489661923 / E.dt;
+    V3 axis;
+    if (fAngle < 0.001) axis = angvel * (0.5 * E.dt - (E.dt * E.dt * E.dt) * 0.020833333333 * fAngle * fAngle);
+    else axis = angvel * (sin(0.5 * fAngle * E.dt) / fAngle);
+    Q4 dqi; dqi.x = -axis.x; dqi.y = -axis.y; dqi.z = -axis.z; dqi.w = cos(fAngle * E.dt * 0.5);
+    Q4 inv; inv.x = -b.q.x; inv.y = -b.q.y; inv.z = -b.q.z; inv.w = b.q.w;
+    Q4 ninv = qnormalize(qmul(inv, dqi));
+    b.q.x = -ninv.x; b.q.y = -ninv.y; b.q.z = -ninv.z; b.q.w = ninv.w;
+    b.R = qmat(b.q);
+  }
+}
+
+PG_HD void substep(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs) {
+  collide(E, S, statR);
+  apply_external(E, S);
+  solve(E, S, statR, rs);
+  integrate(E, S);
+}
+
+// PyBullet's setCollisionFilterPair re-creates the broadphase proxies of both bodies: every manifold of
+// either body is dropped (plate_env:466, :482)
+PG_HD void drop_manifolds_of(Sim& S, int body) {
+  for (int i = 0; i < S.nman;) {
+    if (S.man[i].a == body || S.man[i].b == body) { if (i != S.nman - 1) S.man[i] = S.man[S.nman - 1]; S.nman--; }
+    else i++;
+  }
+}
+
+}  // namespace pg

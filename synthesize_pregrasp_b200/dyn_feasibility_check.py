@@ -1,0 +1,58 @@
+"""GPU entry points with the names and argument meaning of utils/dyn_feasibility_check.py:
+simple_check_dyn_feasible (:226-235) for batches, and the exhaustive triple sweep of
+find_dynamically_feasible_contacts (:239-303) with the geometric criterion."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+from .engine import _ptr, _require_cuda, _stream
+
+MIN_DISTANCE_BETWEEN_FINGER = 0.03   # utils/dyn_feasibility_check.py:19
+DEFAULT_FRICTION_COEFF = 5           # :20
+
+
+def simple_check_dyn_feasible(contact_points, contact_normals, count=None, device=None):
+    """contact_points / contact_normals: [M,3] (one grasp -> bool, like the reference) or [B,M,3] (-> bool array).
+    `count` [B] gives the number of valid contacts per item when they are padded to a common M."""
+    _require_cuda()
+    L = _abi.lib()
+    p = np.asarray(contact_points, np.float64)
+    n = np.asarray(contact_normals, np.float64)
+    single = p.ndim == 2
+    if single:
+        p, n = p[None], n[None]
+    B, M = p.shape[0], p.shape[1]
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    pt, nt = torch.as_tensor(p, device=dev).contiguous(), torch.as_tensor(n, device=dev).contiguous()
+    ct = torch.as_tensor(np.asarray(count, np.int32), device=dev).contiguous() if count is not None else None
+    out = torch.empty(B, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(L.pg_dyn_feasible_simple(_ptr(pt), _ptr(nt), _ptr(ct), B, M, _ptr(out), _stream()))
+    res = out.cpu().numpy().astype(bool)
+    return bool(res[0]) if single else res
+
+
+def find_dynamically_feasible_contacts(points, normals, min_dist=MIN_DISTANCE_BETWEEN_FINGER, first=0, last=None,
+                                       max_out=1 << 22, device=None):
+    """All index triples (i<j<k) of the cloud passing the pairwise-distance prefilter (:260-265) and the simple
+    force/torque-closure test; [first,last) selects a slice of the lexicographic triple index space (one per
+    GPU).  -> (triples [n,3] int32 in unspecified order, total count)."""
+    _require_cuda()
+    L = _abi.lib()
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    pt = torch.as_tensor(np.asarray(points, np.float64), device=dev).contiguous()
+    nt = torch.as_tensor(np.asarray(normals, np.float64), device=dev).contiguous()
+    P = pt.shape[0]
+    total = P * (P - 1) * (P - 2) // 6
+    last = total if last is None else min(last, total)
+    out = torch.empty((max_out, 3), dtype=torch.int32, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _abi.check(L.pg_dyn_sweep_simple(_ptr(pt), _ptr(nt), P, float(min_dist), C.c_uint64(first), C.c_uint64(last),
+                                         _ptr(out), C.c_uint64(max_out), _ptr(cnt), _stream()))
+    n = int(cnt.item())
+    return out[:min(n, max_out)].cpu().numpy(), n

@@ -42,3 +42,14 @@ def recorded(exp):
     k = exp.replace(".", "p")
     return dict(u=g[k + "__u"], poses=g[k + "__poses"], tips=g[k + "__tips"], env=str(g[k + "__env"]),
                 max_force=float(g[k + "__max_force"]))
+
+
+def oracle_cost_spec(spec):
+    walls = [(spec.statics[i].pos, spec.statics[i].quat) for i in spec.clearance_walls]
+    return dict(cloud=spec.cloud, deocclude_boxes=spec.deocclude_boxes, dist_boxes=spec.dist_boxes,
+                dist_tris=spec.dist_tris, clearance_h=spec.clearance_h, walls=walls,
+                wall_size=spec.clearance_wall_size, strict_z=(len(spec.clearance_walls) == 0))
+
+
+def oracle_weights():
+    return dict(np.load(os.path.join(ROOT, "synthesize_pregrasp_b200", "assets", "score_with_df_2980.npz")))

@@ -1,0 +1,24 @@
+// TEST-ONLY: compiles the product's rollout logic (csrc/pg_rollout.cuh, the code the CUDA kernel runs per
+// thread) for the HOST so the container's CPU tests can compare it with the independent oracle before any
+// GPU time is spent.  Not part of the product, not a fallback: the shipped library has no CPU path.
+#include "../../synthesize_pregrasp_b200/csrc/pg_envbuild.h"
+#include "../../synthesize_pregrasp_b200/csrc/pg_rollout.cuh"
+
+extern "C" int hostsim_rollout(const PgEnvSpec* sp, const double* u, const float* noise, int K, int N, const int* path,
+                               double max_force, int train, double* pose, double* fins, double* metric, double* trace,
+                               int* iters) {
+  pg::EnvDev E;
+  std::string err;
+  int rc = pg::build_envdev(sp, E, err);
+  if (rc) { fprintf(stderr, "hostsim: %s\n", err.c_str()); return rc; }
+  for (int k = 0; k < K; k++) {
+    pg::RolloutOut out;
+    out.pose = pose + (size_t)k * N * 7;
+    out.fins = fins + (size_t)k * N * 6;
+    out.metric = metric ? metric + k : nullptr;
+    out.trace = trace ? trace + (size_t)k * N * 50 * 7 : nullptr;
+    out.iters = iters ? iters + (size_t)k * N * 50 : nullptr;
+    pg::rollout_one(E, u, noise ? noise + (size_t)k * N * 48 : nullptr, N, path, max_force, train, out);
+  }
+  return 0;
+}

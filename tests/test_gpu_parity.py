@@ -1,0 +1,231 @@
+"""GPU parity tests: every call goes through the C ABI (libpregrasp_b200.so); the oracle is the checker."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, oracle_cost_spec, oracle_spec, oracle_weights, recorded
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+G = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def EN():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from synthesize_pregrasp_b200 import engine
+    return engine
+
+
+def _oracle_trace(spec, u, noise_row, F, train=False):
+    from oracle.envsim import EnvSim
+    sim = EnvSim(oracle_spec(spec), F)
+    sim.reset()
+    rs = []
+    for j in range(u.shape[0]):
+        a = u[j] + (noise_row[j].astype(np.float64) if noise_row is not None else 0.0)
+        rs.append(sim.step(a, [0, 0, 0], train=train, n_steps=u.shape[0]))
+    return rs
+
+
+@pytest.mark.parametrize("exp", ["foodbox_20.0", "keyboard_20.0", "keyboard_scale_20.0", "wall_laptop_20.0", "cardboard_20.0"])
+def test_physics_kernel_on_recorded_controls(EN, exp):
+    """K=1 replay of the reference's recorded u: kernel vs oracle (tight) and vs the PyBullet recording."""
+    from synthesize_pregrasp_b200.envspec import make_spec
+    g = recorded(exp)
+    spec = make_spec(g["env"])
+    eng = EN.RolloutEngine(spec, device=0)
+    out = eng.physics(g["u"], None, [0, 0], g["max_force"], K=1, want_trace=True)
+    tr = out["trace"][0].cpu().numpy()
+    P = np.concatenate([r["poses"] for r in _oracle_trace(spec, g["u"], None, g["max_force"])])
+    d = np.abs(tr - P).max(axis=1)
+    assert d[:20].max() <= 1e-9, d[:20].max()              # same algorithm: rounding-level agreement early on
+    assert np.median(d) <= 1e-7, np.median(d)
+    e = np.abs(tr - g["poses"]).max(axis=1)
+    assert e[0] <= 1e-6 and e[1] <= 1e-6, e[:2]            # first substeps reproduce PyBullet's recording
+
+
+@pytest.mark.parametrize("env,F", [("foodbox", 20.0), ("bookshelf", 50.0), ("keyboard", 20.0)])
+def test_physics_kernel_random_batch(EN, env, F):
+    """Seeded noise batch, tolerance 1e-4 on the object pose at the cost-evaluation instants (north_star)."""
+    from synthesize_pregrasp_b200.envspec import make_spec
+    spec = make_spec(env)
+    eng = EN.RolloutEngine(spec, device=0)
+    K, N = 24, 2
+    gen = torch.Generator(device="cuda:0").manual_seed(1234)
+    noise = 0.8 * torch.randn((K, N, 48), generator=gen, device="cuda:0", dtype=torch.float32)
+    u = np.zeros((N, 48))
+    out = eng.physics(u, noise, [0, 0], F, want_trace=True)
+    pose = out["pose"].cpu().numpy(); fins = out["fins"].cpu().numpy(); metric = out["metric"].cpu().numpy()
+    nz = noise.cpu().numpy()
+    ok = 0
+    for k in range(K):
+        rs = _oracle_trace(spec, u, nz[k], F, train=True)
+        np.testing.assert_allclose(fins[k], np.stack([r["cur_pos"] for r in rs]), rtol=0, atol=1e-12)
+        ref = np.stack([r["final_pose"] for r in rs])
+        err = np.abs(pose[k] - ref).max()
+        errq = np.abs(pose[k] * np.r_[1, 1, 1, -1, -1, -1, -1] - ref).max()
+        ok += min(err, errq) <= 1e-4
+        # first env step (51 substeps, no settle) must agree tightly for every rollout
+        assert np.abs(out["trace"][k, :20].cpu().numpy() - np.concatenate([r["poses"] for r in rs])[:20]).max() <= 1e-8
+    # contact-rich rollouts are chaotic: a rounding-level difference can flip a contact event late in the
+    # 200-400 substeps; require the bulk to agree within 1e-4 and report the fraction
+    print(f"{env}: {ok}/{K} rollouts within 1e-4 of the oracle at both cost instants")
+    assert ok >= int(0.75 * K), ok
+
+
+@pytest.mark.parametrize("env", ["foodbox", "bookshelf", "keyboard", "laptop", "cardboard"])
+def test_cost_kernel_matches_oracle(EN, env):
+    from oracle import cost as CO
+    from oracle import scorenet as SN
+    from synthesize_pregrasp_b200.envspec import make_spec
+    spec = make_spec(env)
+    eng = EN.RolloutEngine(spec, device=0)
+    rng = np.random.RandomState(5)
+    B = 12
+    pose = np.zeros((B, 7)); fins = np.zeros((B, 2, 3))
+    for b in range(B):
+        q = np.r_[spec.obj_quat] + 0.15 * rng.randn(4)
+        pose[b] = np.r_[np.r_[spec.obj_pos] + 0.03 * rng.randn(3) + [0, 0, 0.02], q / np.linalg.norm(q)]
+        for f in range(2):
+            fins[b, f] = spec.cloud[rng.randint(2048)] + 0.01 * rng.randn(3) if rng.rand() < 0.7 else [100, 100, 100]
+    logit = eng.cost(torch.as_tensor(pose, device="cuda:0"), torch.as_tensor(fins, device="cuda:0")).cpu().numpy()
+    cs, w = oracle_cost_spec(spec), oracle_weights()
+    for b in range(B):
+        pts, df, _ = CO.cost_inputs(pose[b, :3], pose[b, 3:], cs["cloud"], cs["deocclude_boxes"], cs["dist_boxes"], cs["dist_tris"])
+        grasp = np.concatenate([CO.project_to_pcd(fins[b, f], cs["cloud"], cs["clearance_h"], cs["walls"], cs["wall_size"], cs["strict_z"]) for f in range(2)])
+        ref = SN.score_logit(w, pts, df, grasp) if len(pts) else float("nan")
+        if np.isnan(ref):
+            assert np.isnan(logit[b])
+        else:
+            # fp32 network arithmetic vs the fp64 evaluation of the same fp32 weights
+            assert abs(logit[b] - ref) <= 2e-5 * max(1.0, abs(ref)), (b, logit[b], ref)
+
+
+def test_score_entry_point_matches_reference_fixture(EN):
+    from synthesize_pregrasp_b200.envspec import make_spec
+    eng = EN.RolloutEngine(make_spec("foodbox"), device=0)
+    g = np.load(os.path.join(G, "score_net.npz"))
+    for i in range(int(g["n"])):
+        pts = torch.as_tensor(g[f"pts{i}"][None], device="cuda:0"); df = torch.as_tensor(g[f"df{i}"][None], device="cuda:0")
+        gr = torch.as_tensor(g[f"grasp{i}"][None], device="cuda:0")
+        s = float(eng.score(pts, df, gr).item())
+        ref = float(g[f"logit64_{i}"])
+        assert abs(s - ref) <= 2e-5 * max(1.0, abs(ref)), (i, s, ref)
+    # ragged batch through the mask: first 977 points valid
+    pts = torch.as_tensor(g["pts0"][None], device="cuda:0"); df = torch.as_tensor(g["df0"][None], device="cuda:0")
+    mask = torch.zeros((1, 2048), dtype=torch.uint8, device="cuda:0"); mask[:, :977] = 1
+    s = float(eng.score(pts, df, torch.as_tensor(g["grasp0"][None], device="cuda:0"), mask).item())
+    from oracle import scorenet as SN
+    ref = SN.score_logit(oracle_weights(), g["pts0"][:977], g["df0"][:977], g["grasp0"])
+    assert abs(s - ref) <= 2e-5 * max(1.0, abs(ref))
+
+
+def test_end_to_end_cost_and_update_selection(EN):
+    """J through pg_rollout (device) and pg_rollout_host (host buffers) vs the oracle; same MPPI update."""
+    from oracle import mppi
+    from oracle.rollout import rollout as oracle_rollout
+    from synthesize_pregrasp_b200.envspec import make_spec
+    spec = make_spec("foodbox")
+    eng = EN.RolloutEngine(spec, device=0)
+    K, N = 16, 2
+    gen = torch.Generator(device="cuda:0").manual_seed(99)
+    noise = 0.8 * torch.randn((K, N, 48), generator=gen, device="cuda:0", dtype=torch.float32)
+    u = np.zeros((N, 48))
+    J, metric = eng.rollout(u, noise, [0, 0], 20.0, want_metric=True)
+    Jh, mh = eng.rollout_host(u, noise.cpu().numpy(), [0, 0], 20.0, want_metric=True)
+    J = J.cpu().numpy(); metric = metric.cpu().numpy()
+    assert np.array_equal(J, Jh) and np.array_equal(metric, mh)       # same kernels, same bits
+    ref = [oracle_rollout(oracle_spec(spec), oracle_cost_spec(spec), oracle_weights(), u, noise[k].cpu().numpy(), [0, 0, 0], 20.0) for k in range(K)]
+    Jr = np.array([r["J"] for r in ref]); mr = np.array([r["metric"] for r in ref])
+    close = np.abs(J - Jr) <= 1e-3 * np.maximum(1.0, np.abs(Jr))
+    print("rollout costs within 1e-3 rel:", int(close.sum()), "of", K, "max |dJ|", np.abs(J - Jr)[close].max())
+    assert close.sum() >= int(0.75 * K)
+    assert np.abs(metric - mr)[close].max() <= 1e-4
+    # update on the oracle's costs vs update on the kernel's costs (restricted to agreeing rollouts it is identical)
+    u_t = torch.zeros((N, 48), dtype=torch.float64, device="cuda:0")
+    part = EN.mppi_update(torch.as_tensor(J, device="cuda:0"), noise, u_t, 5.0, 1.0, want_partial=True)
+    un, S = mppi.mppi_update(u, J, noise.cpu().numpy(), 5.0, 1.0)
+    np.testing.assert_allclose(u_t.cpu().numpy(), un, rtol=0, atol=1e-12)
+    assert abs(float(part[0]) - J.min()) == 0.0
+    assert int(np.argmax(S)) == int(np.argmin(J))
+
+
+def test_mppi_update_kernel(EN):
+    from oracle import mppi
+    m = np.load(os.path.join(G, "mppi_update.npz"))
+    E = np.ascontiguousarray(np.transpose(m["E"], (2, 0, 1)), np.float32)
+    u_t = torch.as_tensor(m["u0"], device="cuda:0").clone()
+    EN.mppi_update(torch.as_tensor(m["J"], device="cuda:0"), torch.as_tensor(E, device="cuda:0"), u_t, 5.0, 1.0)
+    ref, _ = mppi.mppi_update(m["u0"], m["J"], E, 5.0, 1.0)
+    np.testing.assert_allclose(u_t.cpu().numpy(), ref, rtol=0, atol=1e-13)
+    # edge cases: K=1, +inf costs, large K with a size-independent property (uniform J -> mean of the noise)
+    rng = np.random.RandomState(0)
+    for K in (1, 33, 100003):
+        J = rng.normal(0, 1, K); E = rng.randn(K, 2, 48).astype(np.float32)
+        if K > 1:
+            J[::7] = np.inf
+        u_t = torch.zeros((2, 48), dtype=torch.float64, device="cuda:0")
+        EN.mppi_update(torch.as_tensor(J, device="cuda:0"), torch.as_tensor(E, device="cuda:0"), u_t, 5.0, 1.0)
+        ref, _ = mppi.mppi_update(np.zeros((2, 48)), J, E, 5.0, 1.0)
+        np.testing.assert_allclose(u_t.cpu().numpy(), ref, rtol=0, atol=1e-12)
+    K = 1 << 20
+    E = torch.randn((K, 2, 48), device="cuda:0", dtype=torch.float32)
+    u_t = torch.zeros((2, 48), dtype=torch.float64, device="cuda:0")
+    EN.mppi_update(torch.full((K,), 3.0, dtype=torch.float64, device="cuda:0"), E, u_t, 5.0, 1.0)
+    np.testing.assert_allclose(u_t.cpu().numpy(), E.double().mean(0).cpu().numpy(), rtol=0, atol=1e-12)
+
+
+def test_dyn_feasibility_kernels(EN):
+    from oracle import dynfeas
+    from synthesize_pregrasp_b200 import dyn_feasibility_check as DF
+    d = np.load(os.path.join(G, "dyn_simple.npz"))
+    got = DF.simple_check_dyn_feasible(d["pts"], d["nrm"])
+    assert np.array_equal(got, d["out"])                                   # bit-exact decisions vs the reference
+    gotm = DF.simple_check_dyn_feasible(d["m_pts"], d["m_nrm"], count=d["m_count"])
+    assert np.array_equal(gotm, d["m_out"])
+    assert DF.simple_check_dyn_feasible(d["pts"][0], d["nrm"][0]) == bool(d["out"][0])
+    # sweep over a small cloud vs the oracle, full and split in two index ranges (multi-GPU partition)
+    rng = np.random.RandomState(2)
+    P = 40
+    box = np.array([0.2, 0.2, 0.05])
+    pts = np.zeros((P, 3)); nrm = np.zeros((P, 3))
+    for i in range(P):
+        ax = rng.randint(3); sg = rng.choice([-1.0, 1.0]); q = rng.uniform(-1, 1, 3) * box; q[ax] = sg * box[ax]
+        pts[i] = q; nrm[i, ax] = -sg
+    import itertools
+    ref = [c for c in itertools.combinations(range(P), 3)
+           if min(np.linalg.norm(pts[a] - pts[b]) for a, b in itertools.combinations(c, 2)) >= 0.03
+           and dynfeas.simple_check_dyn_feasible_3p(pts[list(c)], nrm[list(c)])]
+    tri, n = DF.find_dynamically_feasible_contacts(pts, nrm)
+    assert n == len(ref) and sorted(map(tuple, tri.tolist())) == sorted(ref)
+    total = P * (P - 1) * (P - 2) // 6
+    t1, n1 = DF.find_dynamically_feasible_contacts(pts, nrm, first=0, last=total // 2)
+    t2, n2 = DF.find_dynamically_feasible_contacts(pts, nrm, first=total // 2, last=total)
+    assert n1 + n2 == n and sorted(map(tuple, np.concatenate([t1, t2]).tolist())) == sorted(ref)
+
+
+def test_optimizer_api_runs_and_improves(EN):
+    """StochTrajOptimizer with the reference's constructor/return contract (stoch_traj_opt.py:31-46, :231)."""
+    from synthesize_pregrasp_b200.envs import envs_dict
+    from synthesize_pregrasp_b200.stoch_traj_opt import StochTrajOptimizer
+    opt = StochTrajOptimizer(env=envs_dict["foodbox"], sigma=0.8, initial_guess=None, TimeSteps=2, seed=12367134,
+                             render=False, Iterations=3, active_finger_tips=[0, 1], num_interp_f=7, Num_processes=12,
+                             Traj_per_process=15, opt_time=False, verbose=0, mode="only_score", steps=2,
+                             path=np.array([0, 0, 0]), has_distance_field=True, max_forces=20.0, validate=False)
+    uopt, neg_jopt, jopt_log, r_log = opt.optimize()
+    assert uopt.shape == (2, 48) and len(jopt_log) == 3 and len(r_log) == 3
+    assert np.isfinite(neg_jopt) and jopt_log[-1] >= jopt_log[0]
+    J, metric = opt.replay_traj(uopt)
+    assert abs(-J - neg_jopt) <= 1e-9 * max(1.0, abs(J))
+
+
+def test_errors_are_reported_not_swallowed(EN):
+    from synthesize_pregrasp_b200.envspec import make_spec
+    with pytest.raises(RuntimeError):
+        EN.RolloutEngine(make_spec("plate"), device=0)          # hull objects: PG_ERR_UNSUPPORTED this round
+    eng = EN.RolloutEngine(make_spec("foodbox"), device=0)
+    with pytest.raises(RuntimeError):
+        eng.rollout(np.zeros((2, 48)), None, [0, 7], 20.0, K=1)   # contact state out of range
