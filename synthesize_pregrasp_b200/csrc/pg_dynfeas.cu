@@ -8,10 +8,17 @@ namespace pg {
 
 struct D3 { double x, y, z; };
 __device__ __forceinline__ D3 d3(double a, double b, double c) { D3 r; r.x = a; r.y = b; r.z = c; return r; }
-__device__ __forceinline__ D3 sub(D3 a, D3 b) { return d3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ D3 scl(D3 a, double s) { return d3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ double dt3(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ D3 crs(D3 a, D3 b) { return d3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// explicit round-to-nearest mul/add (no FMA contraction): the sign tests below compare products that are exactly
+// zero for axis-aligned contacts, so the arithmetic must be plain IEEE like the reference's numpy ufuncs
+__device__ __forceinline__ D3 sub(D3 a, D3 b) { return d3(__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y), __dsub_rn(a.z, b.z)); }
+__device__ __forceinline__ D3 scl(D3 a, double s) { return d3(__dmul_rn(a.x, s), __dmul_rn(a.y, s), __dmul_rn(a.z, s)); }
+__device__ __forceinline__ double dt3(D3 a, D3 b) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), __dmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ D3 crs(D3 a, D3 b) {
+  return d3(__dsub_rn(__dmul_rn(a.y, b.z), __dmul_rn(a.z, b.y)), __dsub_rn(__dmul_rn(a.z, b.x), __dmul_rn(a.x, b.z)),
+            __dsub_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));
+}
 __device__ __forceinline__ double nrm3(D3 a) { return sqrt(dt3(a, a)); }
 
 __device__ __forceinline__ D3 project2norm(D3 v, D3 n) {        // :124-125
@@ -23,15 +30,25 @@ __device__ __forceinline__ D3 project2norm(D3 v, D3 n) {        // :124-125
 __device__ D3 rotate_axis_angle(D3 aa, D3 p) {
   double ang = nrm3(aa), half = 0.5 * ang, s;
   if (fabs(ang) < 1e-6) s = 0.5 - (ang * ang) / 48; else s = sin(half) / ang;
-  double qw = cos(half), qx = aa.x * s, qy = aa.y * s, qz = aa.z * s;
+  double qw = cos(half), qx = __dmul_rn(aa.x, s), qy = __dmul_rn(aa.y, s), qz = __dmul_rn(aa.z, s);
   // q * (0,p)
-  double tw = -qx * p.x - qy * p.y - qz * p.z;
-  double tx = qw * p.x + qy * p.z - qz * p.y;
-  double ty = qw * p.y - qx * p.z + qz * p.x;
-  double tz = qw * p.z + qx * p.y - qy * p.x;
-  // * conj(q)
-  double ix = -qx, iy = -qy, iz = -qz;
-  return d3(tw * ix + tx * qw + ty * iz - tz * iy, tw * iy - tx * iz + ty * qw + tz * ix, tw * iz + tx * iy - ty * ix + tz * qw);
+#define M_(a, b) __dmul_rn(a, b)
+#define A_(a, b) __dadd_rn(a, b)
+#define S_(a, b) __dsub_rn(a, b)
+  // pytorch3d quaternion_raw_multiply(q, (0,p)) then with conj(q); term order as in the published definition
+  double aw = qw, ax = qx, ay = qy, az = qz, bw = 0.0, bx = p.x, by = p.y, bz = p.z;
+  double tw = S_(S_(S_(M_(aw, bw), M_(ax, bx)), M_(ay, by)), M_(az, bz));
+  double tx = S_(A_(A_(M_(aw, bx), M_(ax, bw)), M_(ay, bz)), M_(az, by));
+  double ty = A_(A_(S_(M_(aw, by), M_(ax, bz)), M_(ay, bw)), M_(az, bx));
+  double tz = A_(S_(A_(M_(aw, bz), M_(ax, by)), M_(ay, bx)), M_(az, bw));
+  double cw = qw, cx = -qx, cy = -qy, cz = -qz;
+  double ox = S_(A_(A_(M_(tw, cx), M_(tx, cw)), M_(ty, cz)), M_(tz, cy));
+  double oy = A_(A_(S_(M_(tw, cy), M_(tx, cz)), M_(ty, cw)), M_(tz, cx));
+  double oz = A_(S_(A_(M_(tw, cz), M_(tx, cy)), M_(ty, cx)), M_(tz, cw));
+#undef M_
+#undef A_
+#undef S_
+  return d3(ox, oy, oz);
 }
 
 __device__ __forceinline__ bool in_triangle(D3 a, D3 b, D3 c) {  // :127-136, point = origin, keeps the `c1<0 and c1<0` typo

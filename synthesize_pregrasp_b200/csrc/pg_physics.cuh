@@ -11,6 +11,9 @@
 // orientation update, dt = 1/250 s.  fp64 throughout: contact-rich rollouts amplify rounding.
 #pragma once
 #include "pg_env.cuh"
+#ifndef PG_BLOCK_THREADS
+#define PG_BLOCK_THREADS 64
+#endif
 
 namespace pg {
 
@@ -44,13 +47,6 @@ struct FixedCons {
   M3 frameB;
   double max_impulse;
   int active;
-};
-
-struct Row {          // one scalar constraint row
-  V3 ax;              // linear jacobian of body A (body B gets -ax)
-  V3 tA, tB;          // angular jacobians
-  V3 wA, wB;          // angular unit-impulse responses (I^-1 t, world frame)
-  double rhs, inv, imp;
 };
 
 struct Sim {
@@ -491,56 +487,100 @@ PG_HD V3 ang_response(const DynBody& b, V3 t) {
   return mul(b.R, al);
 }
 
-struct DV { V3 w, v; };   // accumulated delta velocity of one dynamic body
+// ---------------------------------------------------------------- solver ------------------------------
+// Memory plan of the projected Gauss-Seidel sweep (the dominant cost of a rollout):
+//   * delta velocities of the 3 dynamic bodies (18 doubles) and their world inverse inertias (18 doubles) live
+//     ON CHIP: a per-thread slice of shared memory on the GPU (element i of thread t at sm[i*stride + t],
+//     conflict-free), plain arrays in the host build;
+//   * one record per contact POINT (normal row + both friction rows share the lever arms), 208 B, in
+//     thread-local memory; jacobian cross products and responses are recomputed instead of stored.
+enum { SM_DV = 0, SM_IW = 18, SM_DOUBLES = 36 };
 
-PG_HD double jdot(V3 t, V3 ax, const DV& d) {
+struct PRow {
+  V3 relA, relB, n, l1, l2;
+  double invN, inv1, inv2, denN, den1, den2, rhsN, rhs1, rhs2, impN, imp1, imp2, mu;
+  short a, b, pad0, pad1;
+};
+
+struct NcSet {                 // fingertip servo rows: 6 per active constraint, in solver order
+  double rhs[12], inv[12], den[12], imp[12];
+  V3 col[2][3];                // tip frame axes (angular jacobians) per constraint in solver order
+  short body[2];               // dynamic index (1 or 2) of the constrained tip
+  int n;                       // rows
+};
+
+struct RowSet {
+  PRow pt[MAXPTS];
+  NcSet nc;
+  int n_pts;
+};
+
+// device: the slice lives in dynamic shared memory, addressed directly (LDS/STS, no generic pointer, no aliasing
+// with the thread-local row records); host test build: a plain array
+#if defined(__CUDA_ARCH__)
+extern __shared__ double pg_solver_sm[];
+#define PG_SM(i) pg_solver_sm[(i) * PG_BLOCK_THREADS + threadIdx.x]
+#else
+#define PG_SM(i) sm[(i) * ss]
+#endif
+
+PG_HD V3 sm_w(const double* sm, int ss, int d) { return V3(PG_SM(SM_DV + 6 * d), PG_SM(SM_DV + 6 * d + 1), PG_SM(SM_DV + 6 * d + 2)); }
+PG_HD V3 sm_v(const double* sm, int ss, int d) { return V3(PG_SM(SM_DV + 6 * d + 3), PG_SM(SM_DV + 6 * d + 4), PG_SM(SM_DV + 6 * d + 5)); }
+
+// world inverse inertia (symmetric, 6 doubles: xx xy xz yy yz zz) times t
+PG_HD V3 iw_mul(const double* sm, int ss, int d, V3 t) {
+  const int o = SM_IW + 6 * d;
+  double xx = PG_SM(o), xy = PG_SM(o + 1), xz = PG_SM(o + 2), yy = PG_SM(o + 3), yz = PG_SM(o + 4), zz = PG_SM(o + 5);
+  return V3(xx * t.x + xy * t.y + xz * t.z, xy * t.x + yy * t.y + yz * t.z, xz * t.x + yz * t.y + zz * t.z);
+}
+
+// J . dv for one side of a row:  t . dw + ax . dv   (summed in jacobian order, as the reference engine does)
+PG_HD double side_dot(const double* sm, int ss, int d, V3 t, V3 ax) {
+  V3 w = sm_w(sm, ss, d), v = sm_v(sm, ss, d);
   double s = 0;
-  s += t.x * d.w.x; s += t.y * d.w.y; s += t.z * d.w.z;
-  s += ax.x * d.v.x; s += ax.y * d.v.y; s += ax.z * d.v.z;
+  s += t.x * w.x; s += t.y * w.y; s += t.z * w.z;
+  s += ax.x * v.x; s += ax.y * v.y; s += ax.z * v.z;
   return s;
 }
 
-struct RowSet {
-  Row nc[12];
-  Row normal[MAXPTS];
-  Row fric[2 * MAXPTS];
-  short nA[MAXPTS], nB[MAXPTS];   // body ids per contact point
-  double mu[MAXPTS];
-  int n_nc, n_pts;
-  short nc_body[12];
-};
+// `imass` = 1/mass: the inner loop multiplies by reciprocals (the reference divides; <= 1 ulp apart per term)
+PG_HD void side_apply(double* sm, int ss, int d, V3 t, V3 ax, double imass, double dimp) {
+  V3 r = iw_mul(sm, ss, d, t);
+  double dl = imass * dimp;
+  PG_SM(SM_DV + 6 * d) += r.x * dimp; PG_SM(SM_DV + 6 * d + 1) += r.y * dimp; PG_SM(SM_DV + 6 * d + 2) += r.z * dimp;
+  PG_SM(SM_DV + 6 * d + 3) += ax.x * dl; PG_SM(SM_DV + 6 * d + 4) += ax.y * dl; PG_SM(SM_DV + 6 * d + 5) += ax.z * dl;
+}
 
-PG_HD void setup_contact_row(const EnvDev& E, const Sim& S, Row& r, int bA, int bB, V3 relA, V3 relB, V3 axis,
-                             double dist, bool is_friction) {
-  r.ax = axis;
-  r.tA = cross(relA, axis);
-  r.tB = cross(relB, -axis);
+PG_HD double body_mass(const Sim& S, int d) { return S.dyn[d].mass; }
+
+// effective-mass denominator and relative velocity of one contact row (setup)
+PG_HD void contact_row_setup(const EnvDev& E, const Sim& S, const double* sm, int ss, int bA, int bB, V3 relA, V3 relB, V3 axis,
+                             double dist, bool is_friction, double& inv, double& den, double& rhs) {
   double denom0 = 0, denom1 = 0, rel_vel = 0;
   if (!is_static(bA)) {
     const DynBody& A = S.dyn[bA - MAX_STATICS];
-    r.wA = ang_response(A, r.tA);
-    V3 lin = axis / A.mass;
-    denom0 += r.tA.x * r.wA.x; denom0 += r.tA.y * r.wA.y; denom0 += r.tA.z * r.wA.z;
+    V3 tA = cross(relA, axis), wA = iw_mul(sm, ss, bA - MAX_STATICS, tA), lin = axis / A.mass;
+    denom0 += tA.x * wA.x; denom0 += tA.y * wA.y; denom0 += tA.z * wA.z;
     denom0 += axis.x * lin.x; denom0 += axis.y * lin.y; denom0 += axis.z * lin.z;
     double s = 0;
-    s += A.w.x * r.tA.x; s += A.w.y * r.tA.y; s += A.w.z * r.tA.z;
+    s += A.w.x * tA.x; s += A.w.y * tA.y; s += A.w.z * tA.z;
     s += A.v.x * axis.x; s += A.v.y * axis.y; s += A.v.z * axis.z;
     rel_vel += s;
-  } else r.wA = V3();
+  }
   if (!is_static(bB)) {
     const DynBody& B = S.dyn[bB - MAX_STATICS];
     V3 nax = -axis;
-    r.wB = ang_response(B, r.tB);
-    V3 lin = nax / B.mass;
-    denom1 += r.tB.x * r.wB.x; denom1 += r.tB.y * r.wB.y; denom1 += r.tB.z * r.wB.z;
+    V3 tB = cross(relB, nax), wB = iw_mul(sm, ss, bB - MAX_STATICS, tB), lin = nax / B.mass;
+    denom1 += tB.x * wB.x; denom1 += tB.y * wB.y; denom1 += tB.z * wB.z;
     denom1 += nax.x * lin.x; denom1 += nax.y * lin.y; denom1 += nax.z * lin.z;
     double s = 0;
-    s += B.w.x * r.tB.x; s += B.w.y * r.tB.y; s += B.w.z * r.tB.z;
+    s += B.w.x * tB.x; s += B.w.y * tB.y; s += B.w.z * tB.z;
     s += B.v.x * nax.x; s += B.v.y * nax.y; s += B.v.z * nax.z;
     rel_vel += s;
-  } else r.wB = V3();
+  }
   double d = denom0 + denom1;
-  r.inv = (d > PG_EPS) ? 1.0 / d : 0.0;
+  inv = (d > PG_EPS) ? 1.0 / d : 0.0;
+  den = d;
   double distance = is_friction ? 0.0 : dist + E.slop;
   double positionalError = 0, velocityError = 0 - rel_vel;
   if (is_friction) positionalError = -distance * E.erp2 / E.dt;
@@ -548,8 +588,7 @@ PG_HD void setup_contact_row(const EnvDev& E, const Sim& S, Row& r, int bA, int 
     if (distance > 0) { positionalError = 0; velocityError -= distance / E.dt; }
     else positionalError = -distance * E.erp2 / E.dt;
   }
-  r.rhs = positionalError * r.inv + velocityError * r.inv;
-  r.imp = 0;
+  rhs = positionalError * inv + velocityError * inv;
 }
 
 PG_HD void matrix_to_euler_xyz(const M3& mat, V3& xyz) {
@@ -563,73 +602,37 @@ PG_HD void matrix_to_euler_xyz(const M3& mat, V3& xyz) {
 #undef PG_EL
 }
 
-PG_HD void setup_fixed_rows(const EnvDev& E, const Sim& S, int slot, RowSet& rs) {
+PG_HD void setup_fixed_rows(const EnvDev& E, const Sim& S, const double* sm, int ss, int slot, NcSet& nc) {
   const FixedCons& c = S.cons[slot];
-  const DynBody& A = S.dyn[1 + slot];
+  const int d = 1 + slot;
+  const DynBody& A = S.dyn[d];
   M3 relRot;
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) relRot(i, j) = dot(A.R.col(i), c.frameB.col(j));
   V3 angleDiff;
   matrix_to_euler_xyz(relRot, angleDiff);
+  int k = nc.n / 6;
+  nc.body[k] = (short)d;
   for (int i = 0; i < 6; i++) {
-    Row& r = rs.nc[rs.n_nc];
-    rs.nc_body[rs.n_nc] = (short)(B_TIP0 + slot);
-    rs.n_nc++;
+    int r = nc.n++;
     V3 nl, na;
     double posError;
     if (i < 3) { nl[i] = 1; posError = dot(A.pos - c.pivotB, nl); }
-    else { na = A.R.col(i % 3); posError = angleDiff[i % 3]; }
-    V3 oc = cross(V3(), nl);           // pivot coincides with the tip's centre of mass
-    r.tA = oc + na; r.ax = nl; r.tB = V3(); r.wB = V3();
-    r.wA = ang_response(A, r.tA);
-    V3 lin = nl / A.mass;
-    double d = 0;
-    d += r.tA.x * r.wA.x; d += r.tA.y * r.wA.y; d += r.tA.z * r.wA.z;
-    d += nl.x * lin.x; d += nl.y * lin.y; d += nl.z * lin.z;
-    r.inv = (d > PG_EPS) ? 1.0 / d : 0.0;
+    else { na = A.R.col(i % 3); nc.col[k][i % 3] = na; posError = angleDiff[i % 3]; }
+    V3 wA = iw_mul(sm, ss, d, na), lin = nl / A.mass;
+    double dd = 0;
+    dd += na.x * wA.x; dd += na.y * wA.y; dd += na.z * wA.z;
+    dd += nl.x * lin.x; dd += nl.y * lin.y; dd += nl.z * lin.z;
+    double inv = (dd > PG_EPS) ? 1.0 / dd : 0.0;
     double rel_vel = 0;
-    rel_vel += A.w.x * r.tA.x; rel_vel += A.w.y * r.tA.y; rel_vel += A.w.z * r.tA.z;
+    rel_vel += A.w.x * na.x; rel_vel += A.w.y * na.y; rel_vel += A.w.z * na.z;
     rel_vel += A.v.x * nl.x; rel_vel += A.v.y * nl.y; rel_vel += A.v.z * nl.z;
     double velocityError = (0 - rel_vel) * 1.0;
     double positionalError = -posError * E.erp / E.dt;
-    r.rhs = positionalError * r.inv + velocityError * r.inv;
-    r.imp = 0;
+    nc.rhs[r] = positionalError * inv + velocityError * inv;
+    nc.inv[r] = inv;
+    nc.den[r] = dd;
+    nc.imp[r] = 0;
   }
-}
-
-// delta impulse of a row against the current delta-velocities
-PG_HD double row_delta(const Row& r, int bA, int bB, const DV* dv) {
-  double delta = r.rhs;   // cfm = 0
-  double a = 0, b = 0;
-  if (bA >= MAX_STATICS) a = jdot(r.tA, r.ax, dv[bA - MAX_STATICS]);
-  if (bB >= MAX_STATICS) b = jdot(r.tB, -r.ax, dv[bB - MAX_STATICS]);
-  delta -= a * r.inv;
-  delta -= b * r.inv;
-  return delta;
-}
-
-PG_HD void row_apply(const Sim& S, const Row& r, int bA, int bB, DV* dv, double dimp) {
-  if (bA >= MAX_STATICS) {
-    DV& d = dv[bA - MAX_STATICS];
-    double im = S.dyn[bA - MAX_STATICS].mass;
-    d.w.x += r.wA.x * dimp; d.w.y += r.wA.y * dimp; d.w.z += r.wA.z * dimp;
-    d.v.x += (r.ax.x / im) * dimp; d.v.y += (r.ax.y / im) * dimp; d.v.z += (r.ax.z / im) * dimp;
-  }
-  if (bB >= MAX_STATICS) {
-    DV& d = dv[bB - MAX_STATICS];
-    double im = S.dyn[bB - MAX_STATICS].mass;
-    d.w.x += r.wB.x * dimp; d.w.y += r.wB.y * dimp; d.w.z += r.wB.z * dimp;
-    d.v.x += (-r.ax.x / im) * dimp; d.v.y += (-r.ax.y / im) * dimp; d.v.z += (-r.ax.z / im) * dimp;
-  }
-}
-
-PG_HD double resolve_row(const Sim& S, Row& r, int bA, int bB, DV* dv, double lo, double hi) {
-  double delta = row_delta(r, bA, bB, dv);
-  double sum = r.imp + delta;
-  if (sum < lo) { delta = lo - r.imp; r.imp = lo; }
-  else if (sum > hi) { delta = hi - r.imp; r.imp = hi; }
-  else r.imp = sum;
-  row_apply(S, r, bA, bB, dv, delta);
-  return delta / r.inv;
 }
 
 // btAlignedObjectArray::quickSortInternal on (key, payload) pairs, explicit stack
@@ -652,7 +655,7 @@ PG_HD void bt_quicksort(int* key, int* val, int n) {
   }
 }
 
-PG_HDN void solve(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs) {
+PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* __restrict__ statR, RowSet& __restrict__ rs, double* sm, int ss) {
   // islands over the (overlapping-pair) manifolds; tags: obj 0, tip0 1, tip1 2
   int uf[3] = {0, 1, 2};
   for (int k = 0; k < S.nman; k++) {
@@ -677,7 +680,22 @@ PG_HDN void solve(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs) {
   for (int c = 0; c < 2; c++) if (S.cons[c].active) { ckey[ncons] = tag[1 + c]; cval[ncons] = c; ncons++; }
   bt_quicksort(ckey, cval, ncons);
 
-  rs.n_nc = 0; rs.n_pts = 0;
+  // on-chip state: zero delta velocities, world inverse inertias  R diag(1/I) R^T
+  for (int i = 0; i < 18; i++) PG_SM(SM_DV + i) = 0.0;
+  for (int d = 0; d < 3; d++) {
+    const DynBody& b = S.dyn[d];
+    double ix = 1.0 / b.inertia.x, iy = 1.0 / b.inertia.y, iz = 1.0 / b.inertia.z;
+    const M3& R = b.R;
+    const int o = SM_IW + 6 * d;
+    PG_SM(o) = R(0, 0) * R(0, 0) * ix + R(0, 1) * R(0, 1) * iy + R(0, 2) * R(0, 2) * iz;
+    PG_SM(o + 1) = R(0, 0) * R(1, 0) * ix + R(0, 1) * R(1, 1) * iy + R(0, 2) * R(1, 2) * iz;
+    PG_SM(o + 2) = R(0, 0) * R(2, 0) * ix + R(0, 1) * R(2, 1) * iy + R(0, 2) * R(2, 2) * iz;
+    PG_SM(o + 3) = R(1, 0) * R(1, 0) * ix + R(1, 1) * R(1, 1) * iy + R(1, 2) * R(1, 2) * iz;
+    PG_SM(o + 4) = R(1, 0) * R(2, 0) * ix + R(1, 1) * R(2, 1) * iy + R(1, 2) * R(2, 2) * iz;
+    PG_SM(o + 5) = R(2, 0) * R(2, 0) * ix + R(2, 1) * R(2, 1) * iy + R(2, 2) * R(2, 2) * iz;
+  }
+
+  rs.nc.n = 0; rs.n_pts = 0;
   for (int o = 0; o < S.nman; o++) {
     const Manifold& m = S.man[mval[o]];
     BodyView A = view(E, S, statR, m.a), B = view(E, S, statR, m.b);
@@ -687,59 +705,101 @@ PG_HDN void solve(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs) {
     for (int k = 0; k < m.n && rs.n_pts < MAXPTS; k++) {
       const MPoint& cp = m.p[k];
       V3 posA = mul(A.R, cp.localA) + A.pos, posB = mul(B.R, cp.localB) + B.pos;
-      V3 relA = posA - A.pos, relB = posB - B.pos;
-      int idx = rs.n_pts++;
-      rs.nA[idx] = m.a; rs.nB[idx] = m.b; rs.mu[idx] = f;
-      setup_contact_row(E, S, rs.normal[idx], m.a, m.b, relA, relB, cp.normalB, cp.dist, false);
+      PRow& r = rs.pt[rs.n_pts++];
+      r.relA = posA - A.pos; r.relB = posB - B.pos; r.n = cp.normalB; r.a = m.a; r.b = m.b; r.mu = f;
       V3 l1, l2;
       plane_space1(cp.normalB, l1, l2);
-      l1 = l1 / len(l1);
-      l2 = l2 / len(l2);
-      setup_contact_row(E, S, rs.fric[2 * idx], m.a, m.b, relA, relB, l1, 0.0, true);
-      setup_contact_row(E, S, rs.fric[2 * idx + 1], m.a, m.b, relA, relB, l2, 0.0, true);
+      r.l1 = l1 / len(l1);
+      r.l2 = l2 / len(l2);
+      contact_row_setup(E, S, sm, ss, m.a, m.b, r.relA, r.relB, r.n, cp.dist, false, r.invN, r.denN, r.rhsN);
+      contact_row_setup(E, S, sm, ss, m.a, m.b, r.relA, r.relB, r.l1, 0.0, true, r.inv1, r.den1, r.rhs1);
+      contact_row_setup(E, S, sm, ss, m.a, m.b, r.relA, r.relB, r.l2, 0.0, true, r.inv2, r.den2, r.rhs2);
+      r.impN = 0; r.imp1 = 0; r.imp2 = 0;
     }
   }
-  for (int c = 0; c < ncons; c++) setup_fixed_rows(E, S, cval[c], rs);
+  for (int c = 0; c < ncons; c++) setup_fixed_rows(E, S, sm, ss, cval[c], rs.nc);
   S.last_iterations = 0;
-  if (rs.n_nc == 0 && rs.n_pts == 0) return;
+  if (rs.nc.n == 0 && rs.n_pts == 0) return;
+  double max_imp[2] = {0, 0};
+  for (int c = 0; c < ncons; c++) max_imp[c] = S.cons[cval[c]].max_impulse;
+  const double m_obj = 1.0 / S.dyn[0].mass, m_tip = 1.0 / S.dyn[1].mass;   // inverse masses
 
-  DV dv[3];
   int it;
   for (it = 0; it < E.iterations; it++) {
     double lsr = 0;
-    int nn = rs.n_nc;
+    // ---- fingertip servo rows, alternating sweep direction
+    const int nn = rs.nc.n;
     for (int j = 0; j < nn; j++) {
       int index = (it & 1) ? j : nn - 1 - j;
-      int body = rs.nc_body[index];
-      double mi = S.cons[body - B_TIP0].max_impulse;
-      double res = resolve_row(S, rs.nc[index], body, -1, dv, -mi, mi);
+      int c = index / 6, i = index - 6 * c, d = rs.nc.body[c];
+      double inv = rs.nc.inv[index], imp = rs.nc.imp[index], delta = rs.nc.rhs[index], mi = max_imp[c];
+      const double den = rs.nc.den[index];
+      if (i < 3) {
+        double a = 0;
+        a += PG_SM(SM_DV + 6 * d + 3 + i);            // jacobian = unit vector e_i on the linear part
+        delta -= a * inv;
+      } else {
+        V3 na = rs.nc.col[c][i - 3];
+        delta -= side_dot(sm, ss, d, na, V3()) * inv;
+      }
+      double sum = imp + delta;
+      if (sum < -mi) { delta = -mi - imp; imp = -mi; }
+      else if (sum > mi) { delta = mi - imp; imp = mi; }
+      else imp = sum;
+      rs.nc.imp[index] = imp;
+      if (i < 3) PG_SM(SM_DV + 6 * d + 3 + i) += m_tip * delta;
+      else side_apply(sm, ss, d, rs.nc.col[c][i - 3], V3(), m_tip, delta);
+      double res = delta * den;            // = delta / inv, the velocity change of this row
       lsr = fmax(lsr, res * res);
     }
+    // ---- normal rows
     for (int k = 0; k < rs.n_pts; k++) {
-      double res = resolve_row(S, rs.normal[k], rs.nA[k], rs.nB[k], dv, 0.0, 1e10);
+      PRow& r = rs.pt[k];
+      const int da = r.a - MAX_STATICS, db = r.b - MAX_STATICS;
+      V3 n = r.n, tA = cross(r.relA, n), tB = cross(r.relB, -n);
+      double delta = r.rhsN, a = 0, b = 0;
+      if (da >= 0) a = side_dot(sm, ss, da, tA, n);
+      if (db >= 0) b = side_dot(sm, ss, db, tB, -n);
+      delta -= a * r.invN;
+      delta -= b * r.invN;
+      double sum = r.impN + delta;
+      if (sum < 0.0) { delta = 0.0 - r.impN; r.impN = 0.0; }
+      else if (sum > 1e10) { delta = 1e10 - r.impN; r.impN = 1e10; }
+      else r.impN = sum;
+      if (da >= 0) side_apply(sm, ss, da, tA, n, da == 0 ? m_obj : m_tip, delta);
+      if (db >= 0) side_apply(sm, ss, db, tB, -n, db == 0 ? m_obj : m_tip, delta);
+      double res = delta * r.denN;
       lsr = fmax(lsr, res * res);
     }
+    // ---- friction pairs with the implicit cone
     for (int k = 0; k < rs.n_pts; k++) {
-      Row& cA = rs.fric[2 * k];
-      Row& cB = rs.fric[2 * k + 1];
-      int bA = rs.nA[k], bB = rs.nB[k];
-      double lim = rs.mu[k] * rs.normal[k].imp;
-      double loA = -lim, loB = -lim;
-      double dB = row_delta(cB, bA, bB, dv), sumB = cB.imp + dB;
-      double dA = row_delta(cA, bA, bB, dv), sumA = cA.imp + dA;
-      if (sumA * sumA + sumB * sumB >= loA * loB) {
-        double angle = atan2(sumA, sumB);
-        double ca = fabs(loA * sin(angle)), cb = fabs(loB * cos(angle));
-        if (sumA < -ca) { dA = -ca - cA.imp; cA.imp = -ca; }
-        else if (sumA > ca) { dA = ca - cA.imp; cA.imp = ca; }
-        else cA.imp = sumA;
-        if (sumB < -cb) { dB = -cb - cB.imp; cB.imp = -cb; }
-        else if (sumB > cb) { dB = cb - cB.imp; cB.imp = cb; }
-        else cB.imp = sumB;
-      } else { cA.imp = sumA; cB.imp = sumB; }
-      row_apply(S, cA, bA, bB, dv, dA);
-      row_apply(S, cB, bA, bB, dv, dB);
-      double res = dA / cA.inv + dB / cB.inv;
+      PRow& r = rs.pt[k];
+      const int da = r.a - MAX_STATICS, db = r.b - MAX_STATICS;
+      V3 l1 = r.l1, l2 = r.l2;
+      V3 tA1 = cross(r.relA, l1), tB1 = cross(r.relB, -l1), tA2 = cross(r.relA, l2), tB2 = cross(r.relB, -l2);
+      double lim = r.mu * r.impN, lo = -lim;
+      double dB = r.rhs2, dA = r.rhs1, a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+      if (da >= 0) { a2 = side_dot(sm, ss, da, tA2, l2); a1 = side_dot(sm, ss, da, tA1, l1); }
+      if (db >= 0) { b2 = side_dot(sm, ss, db, tB2, -l2); b1 = side_dot(sm, ss, db, tB1, -l1); }
+      dB -= a2 * r.inv2; dB -= b2 * r.inv2;
+      dA -= a1 * r.inv1; dA -= b1 * r.inv1;
+      double sumB = r.imp2 + dB, sumA = r.imp1 + dA;
+      if (sumA * sumA + sumB * sumB >= lo * lo) {
+        // |lo*sin(atan2(a,b))| = |lo*a|/hypot, |lo*cos(atan2(a,b))| = |lo*b|/hypot: same clip without transcendentals
+        double rinv = 1.0 / sqrt(sumA * sumA + sumB * sumB);
+        double ca = fabs(lo * sumA * rinv), cb = fabs(lo * sumB * rinv);
+        if (sumA < -ca) { dA = -ca - r.imp1; r.imp1 = -ca; }
+        else if (sumA > ca) { dA = ca - r.imp1; r.imp1 = ca; }
+        else r.imp1 = sumA;
+        if (sumB < -cb) { dB = -cb - r.imp2; r.imp2 = -cb; }
+        else if (sumB > cb) { dB = cb - r.imp2; r.imp2 = cb; }
+        else r.imp2 = sumB;
+      } else { r.imp1 = sumA; r.imp2 = sumB; }
+      if (da >= 0) side_apply(sm, ss, da, tA1, l1, da == 0 ? m_obj : m_tip, dA);
+      if (db >= 0) side_apply(sm, ss, db, tB1, -l1, db == 0 ? m_obj : m_tip, dA);
+      if (da >= 0) side_apply(sm, ss, da, tA2, l2, da == 0 ? m_obj : m_tip, dB);
+      if (db >= 0) side_apply(sm, ss, db, tB2, -l2, db == 0 ? m_obj : m_tip, dB);
+      double res = dA * r.den1 + dB * r.den2;
       lsr = fmax(lsr, res * res);
     }
     if (lsr <= E.residual_threshold || it >= E.iterations - 1) { it++; break; }
@@ -747,8 +807,9 @@ PG_HDN void solve(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs) {
   S.last_iterations = it;
   for (int d = 0; d < 3; d++) {
     DynBody& b = S.dyn[d];
-    b.w.x += dv[d].w.x; b.w.y += dv[d].w.y; b.w.z += dv[d].w.z;
-    b.v.x += dv[d].v.x; b.v.y += dv[d].v.y; b.v.z += dv[d].v.z;
+    V3 w = sm_w(sm, ss, d), v = sm_v(sm, ss, d);
+    b.w.x += w.x; b.w.y += w.y; b.w.z += w.z;
+    b.v.x += v.x; b.v.y += v.y; b.v.z += v.z;
   }
 }
 
@@ -771,10 +832,10 @@ PG_HD void integrate(const EnvDev& E, Sim& S) {
   }
 }
 
-PG_HD void substep(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs) {
+PG_HD void substep(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, double* sm, int ss) {
   collide(E, S, statR);
   apply_external(E, S);
-  solve(E, S, statR, rs);
+  solve(E, S, statR, rs, sm, ss);
   integrate(E, S);
 }
 

@@ -6,12 +6,14 @@
 // latency on every row; a thread per rollout keeps all 32 lanes busy with independent rollouts and the only
 // divergence is the per-rollout row count.  HBM sees u + noise in and pose/fins/metric out; everything else
 // (bodies, manifolds, solver rows) lives in registers and thread-local memory for the whole rollout.
+#define PG_BLOCK_THREADS 64
 #include "pg_internal.h"
 #include "pg_rollout.cuh"
 
 namespace pg {
 
-__global__ void __launch_bounds__(64) rollout_kernel(const EnvDev* __restrict__ env, const double* __restrict__ u,
+#define RK_THREADS PG_BLOCK_THREADS
+__global__ void __launch_bounds__(RK_THREADS, 7) rollout_kernel(const EnvDev* __restrict__ env, const double* __restrict__ u,
                                                       const float* __restrict__ noise, int K, int N,
                                                       const int* __restrict__ path, double max_force,
                                                       double* __restrict__ pose, double* __restrict__ fins,
@@ -25,14 +27,14 @@ __global__ void __launch_bounds__(64) rollout_kernel(const EnvDev* __restrict__ 
   out.metric = metric ? metric + k : nullptr;
   out.trace = trace ? trace + (size_t)k * N * SKIP * 7 : nullptr;
   out.iters = iters ? iters + (size_t)k * N * SKIP : nullptr;
-  rollout_one(*env, u, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path, max_force, 1, out);
+  rollout_one(*env, u, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path, max_force, 1, out, nullptr, 0);   // solver slice: dynamic shared memory, see PG_SM
 }
 
 int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
                    double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st) {
-  const int threads = 64;
+  const int threads = RK_THREADS;
   int blocks = (K + threads - 1) / threads;
-  rollout_kernel<<<blocks, threads, 0, st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
+  rollout_kernel<<<blocks, threads, SM_DOUBLES * RK_THREADS * sizeof(double), st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
   count_launch();
   PG_CUDA(cudaGetLastError());
   return PG_OK;

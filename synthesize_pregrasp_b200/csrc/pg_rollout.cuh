@@ -148,8 +148,9 @@ struct RolloutOut {
   int* iters;         // optional [N*SKIP]
 };
 
+// sm / ss: the thread's on-chip solver slice (element i at sm[i*ss]); SM_DOUBLES elements
 PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, int N, const int* path,
-                        double max_force, int train, RolloutOut out) {
+                        double max_force, int train, RolloutOut out, double* sm, int ss) {
   Sim S;
   RowSet rs;
   M3 statR[MAX_STATICS];
@@ -175,7 +176,7 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
   }
   S.nman = 0; S.filter_off = 0; S.obj_first = 1; S.last_iterations = 0;
   S.cons[0].active = 0; S.cons[1].active = 0;
-  substep(E, S, statR, rs);                                                       // :237
+  substep(E, S, statR, rs, sm, ss);                                                       // :237
   S.obj_first = 0;
   Carry carry;
   for (int f = 0; f < NFING; f++) { carry.on[f] = 0; carry.pos[f] = V3(); carry.norm[f] = V3(); }
@@ -201,7 +202,7 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
         t.pos = g; t.q = qnormalize(o.q); t.v = V3(); t.w = V3(); t.R = qmat(t.q);
         S.cons[i].pivotB = g; S.cons[i].frameB = R; S.cons[i].max_impulse = E.default_max_impulse; S.cons[i].active = 1;
       }
-      substep(E, S, statR, rs);
+      substep(E, S, statR, rs, sm, ss);
       for (int i = 0; i < NFING; i++) {
         S.filter_off &= ~(1u << i);
         drop_manifolds_of(S, B_TIP0 + i);
@@ -223,13 +224,13 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
         V3 tar = (o.pos + mul(R, cur_pos[i])) + v_g;
         S.cons[i].pivotB = tar; S.cons[i].frameB = R; S.cons[i].max_impulse = max_force * E.dt;
       }
-      substep(E, S, statR, rs);
+      substep(E, S, statR, rs, sm, ss);
       if (out.iters) out.iters[j * SKIP + t] = S.last_iterations;
     }
     // ---- settle + metric :556-603 (train mode)
     if (j == N - 1 && train) {
       double m0 = (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
-      for (int s = 0; s < E.settle_substeps; s++) substep(E, S, statR, rs);
+      for (int s = 0; s < E.settle_substeps; s++) substep(E, S, statR, rs, sm, ss);
       if (out.metric) *out.metric = m0 + (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
     }
     DynBody& o = S.dyn[0];

@@ -119,7 +119,8 @@ class RolloutEngine:
 
     def physics(self, u, noise, path, max_force, K=None, want_trace=False, want_iters=False):
         with torch.cuda.device(self.device):
-            u_t = torch.as_tensor(np.asarray(u, np.float64), dtype=torch.float64, device=self._dev()).contiguous()
+            u_t = torch.as_tensor(np.asarray(u, np.float64) if not torch.is_tensor(u) else u, dtype=torch.float64,
+                                  device=self._dev()).contiguous()
             N = u_t.shape[0]
             if noise is not None:
                 K = noise.shape[0]

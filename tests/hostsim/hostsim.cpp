@@ -18,7 +18,8 @@ extern "C" int hostsim_rollout(const PgEnvSpec* sp, const double* u, const float
     out.metric = metric ? metric + k : nullptr;
     out.trace = trace ? trace + (size_t)k * N * 50 * 7 : nullptr;
     out.iters = iters ? iters + (size_t)k * N * 50 : nullptr;
-    pg::rollout_one(E, u, noise ? noise + (size_t)k * N * 48 : nullptr, N, path, max_force, train, out);
+    double sm[pg::SM_DOUBLES];
+    pg::rollout_one(E, u, noise ? noise + (size_t)k * N * 48 : nullptr, N, path, max_force, train, out, sm, 1);
   }
   return 0;
 }
