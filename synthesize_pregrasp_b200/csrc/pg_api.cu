@@ -1,6 +1,8 @@
 // C ABI (include/pregrasp_b200.h): handle management, constant upload, host-buffer wrappers.
 #include <math.h>
 #include <string.h>
+#include <stddef.h>
+#include <stdlib.h>
 #include <atomic>
 #include <vector>
 #include "pg_internal.h"
@@ -73,6 +75,15 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   for (int j = 0; j < C1; j++) w1d[j] = W.conv1_w[4 * j + 3];
   for (int c = 0; c < C2; c++) for (int j = 0; j < C1; j++) w2t[j * C2 + c] = W.conv2_w[c * C1 + j];
   for (int o = 0; o < C3; o++) for (int k = 0; k < C2; k++) { w3at[k * C3 + o] = W.conv3_w[o * 2 * C2 + k]; w3bt[k * C3 + o] = W.conv3_w[o * 2 * C2 + C2 + k]; }
+  // tensor-core operands: W3a split into tf32 hi + lo, canonical K-major layout [(k/4)][n][k%4]
+  std::vector<float> w3hi(C2 * C3), w3lo(C2 * C3);
+  auto tf32_rna = [](float x) { uint32_t u; memcpy(&u, &x, 4); u += 0x1000u; u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; };
+  for (int n = 0; n < C3; n++) for (int k = 0; k < C2; k++) {
+    float wv = W.conv3_w[n * 2 * C2 + k], hi = tf32_rna(wv);
+    size_t idx = ((size_t)(k / 4) * C3 + n) * 4 + (k % 4);
+    w3hi[idx] = hi; w3lo[idx] = wv - hi;
+  }
+  e->use_tensor_cores = getenv("PG_COST_FFMA") ? 0 : 1;
   Blob b;
   size_t o_env = b.add(&E, sizeof(EnvDev));
   size_t o_cloud = b.add(sp->cloud, sizeof(double) * 3 * P_CLOUD);
@@ -82,6 +93,7 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   size_t o_f1w = b.add(W.fc1_w, F1 * LAT * 4), o_f1b = b.add(W.fc1_b, F1 * 4), o_f2w = b.add(W.fc2_w, F2 * F1 * 4), o_f2b = b.add(W.fc2_b, F2 * 4);
   size_t o_f3w = b.add(W.fc3_w, F3 * F2 * 4), o_f3b = b.add(W.fc3_b, F3 * 4), o_ow = b.add(W.out_w, F3 * 4), o_ob = b.add(W.out_b, 4);
   size_t o_w1 = b.add(W.conv1_w, C1 * 4 * 4), o_b1 = b.add(W.conv1_b, C1 * 4);
+  size_t o_w3hi = b.add(w3hi.data(), w3hi.size() * 4), o_w3lo = b.add(w3lo.data(), w3lo.size() * 4);
   size_t o_tri = sp->n_dist_tri > 0 ? b.add(sp->dist_tri, sizeof(double) * 9 * sp->n_dist_tri) : 0;
   unsigned char* d = nullptr;
   cudaError_t ce = cudaMalloc(&d, b.h.size());
@@ -97,6 +109,7 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   c.b3 = FP(o_b3); c.w4 = FP(o_w4); c.b4 = FP(o_b4); c.fc1_w = FP(o_f1w); c.fc1_b = FP(o_f1b); c.fc2_w = FP(o_f2w);
   c.fc2_b = FP(o_f2b); c.fc3_w = FP(o_f3w); c.fc3_b = FP(o_f3b); c.out_w = FP(o_ow); c.out_b = FP(o_ob);
   c.w1 = FP(o_w1); c.b1 = FP(o_b1);
+  e->w3a_hi = FP(o_w3hi); e->w3a_lo = FP(o_w3lo);
 #undef FP
   c.n_cloud = P_CLOUD; c.n_crop = sp->n_crop; c.n_dist_box = sp->n_dist_box; c.n_dist_tri = sp->n_dist_tri;
   memcpy(c.crop, sp->crop, sizeof(c.crop));

@@ -477,7 +477,21 @@ static int sm_count(int device) {
   return n;
 }
 
+int launch_mlp(PgEnv* env, const float* latent, int B, float* logit, cudaStream_t st) {
+  int g2 = (B + MLP_G - 1) / MLP_G;
+  if (g2 > 4 * sm_count(env->device)) g2 = 4 * sm_count(env->device);
+  mlp_kernel<<<g2, 256, 0, st>>>(env->cost, latent, B, logit);
+  count_launch();
+  PG_CUDA(cudaGetLastError());
+  return PG_OK;
+}
+
 int launch_cost(PgEnv* env, const double* pose, const double* fins, int B, float* latent, float* logit, cudaStream_t st) {
+  if (env->use_tensor_cores && env->cost.n_dist_tri == 0) {
+    int rc = launch_cost_tc(env, pose, fins, B, latent, st);
+    if (rc) return rc;
+    return launch_mlp(env, latent, B, logit, st);
+  }
   size_t smem = sizeof(Smem);
   static bool attr_set = false;
   if (!attr_set) {

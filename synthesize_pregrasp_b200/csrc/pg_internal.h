@@ -42,6 +42,8 @@ struct PgEnv {
   pg::EnvDev* dev_env;
   pg::CostDev cost;
   void* blob;                    // one allocation holding every constant table
+  const float *w3a_hi, *w3a_lo;  // conv3 point-half weights, tf32 hi/lo split, UMMA canonical K-major layout
+  int use_tensor_cores;
   // scratch (grown on demand)
   double *pose, *fins;           // [K,N,7], [K,N,2,3]
   float* logit;                  // [K*N]
@@ -62,5 +64,7 @@ int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N
 int launch_cost(PgEnv* env, const double* pose, const double* fins, int B, float* latent, float* logit, cudaStream_t st);
 int launch_score(PgEnv* env, const float* pts, const float* df, const uint8_t* mask, const float* grasp, int B, int P,
                  float* latent, float* logit, cudaStream_t st);
+int launch_cost_tc(PgEnv* env, const double* pose, const double* fins, int B, float* latent, cudaStream_t st);
+int launch_mlp(PgEnv* env, const float* latent, int B, float* logit, cudaStream_t st);
 int launch_accumulate_cost(const float* logit, int K, int N, double* J, cudaStream_t st);
 }

@@ -551,7 +551,12 @@ PG_HD void side_apply(double* sm, int ss, int d, V3 t, V3 ax, double imass, doub
   PG_SM(SM_DV + 6 * d + 3) += ax.x * dl; PG_SM(SM_DV + 6 * d + 4) += ax.y * dl; PG_SM(SM_DV + 6 * d + 5) += ax.z * dl;
 }
 
-PG_HD double body_mass(const Sim& S, int d) { return S.dyn[d].mass; }
+// apply an already-scaled angular impulse `tq` and linear impulse `li`
+PG_HD void side_apply2(double* sm, int ss, int d, V3 tq, V3 li, double imass) {
+  V3 r = iw_mul(sm, ss, d, tq);
+  PG_SM(SM_DV + 6 * d) += r.x; PG_SM(SM_DV + 6 * d + 1) += r.y; PG_SM(SM_DV + 6 * d + 2) += r.z;
+  PG_SM(SM_DV + 6 * d + 3) += li.x * imass; PG_SM(SM_DV + 6 * d + 4) += li.y * imass; PG_SM(SM_DV + 6 * d + 5) += li.z * imass;
+}
 
 // effective-mass denominator and relative velocity of one contact row (setup)
 PG_HD void contact_row_setup(const EnvDev& E, const Sim& S, const double* sm, int ss, int bA, int bB, V3 relA, V3 relB, V3 axis,
@@ -795,10 +800,10 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
         else if (sumB > cb) { dB = cb - r.imp2; r.imp2 = cb; }
         else r.imp2 = sumB;
       } else { r.imp1 = sumA; r.imp2 = sumB; }
-      if (da >= 0) side_apply(sm, ss, da, tA1, l1, da == 0 ? m_obj : m_tip, dA);
-      if (db >= 0) side_apply(sm, ss, db, tB1, -l1, db == 0 ? m_obj : m_tip, dA);
-      if (da >= 0) side_apply(sm, ss, da, tA2, l2, da == 0 ? m_obj : m_tip, dB);
-      if (db >= 0) side_apply(sm, ss, db, tB2, -l2, db == 0 ? m_obj : m_tip, dB);
+      // both deltas were computed against the same velocities (Jacobi inside the pair), so the two impulses of a
+      // body are applied as ONE combined linear + angular impulse (one inverse-inertia product per body)
+      if (da >= 0) side_apply2(sm, ss, da, tA1 * dA + tA2 * dB, l1 * dA + l2 * dB, da == 0 ? m_obj : m_tip);
+      if (db >= 0) side_apply2(sm, ss, db, tB1 * dA + tB2 * dB, -(l1 * dA + l2 * dB), db == 0 ? m_obj : m_tip);
       double res = dA * r.den1 + dB * r.den2;
       lsr = fmax(lsr, res * res);
     }
