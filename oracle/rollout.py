@@ -7,7 +7,7 @@ from . import scorenet as SN
 from .envsim import EnvSim
 
 
-def rollout(spec, cost_spec, weights, u, noise_row, path, max_force, params=None):
+def rollout(spec, cost_spec, weights, u, noise_row, path, max_force, params=None, net_dtype=np.float64):
     """spec: EnvSim dict; cost_spec: dict(cloud, deocclude_boxes, dist_boxes, dist_tris, clearance_h,
     walls=[(pos,quat)], wall_size, strict_z); u [N,48]; noise_row [N,48] or None.
     -> dict(J, metric, poses [N,7], fins [N,2,3], logits [N], trace [N*50,7])"""
@@ -25,7 +25,7 @@ def rollout(spec, cost_spec, weights, u, noise_row, path, max_force, params=None
         grasp = np.concatenate([CO.project_to_pcd(r["cur_pos"][f], cost_spec["cloud"], cost_spec["clearance_h"],
                                                   cost_spec["walls"], cost_spec["wall_size"], cost_spec["strict_z"])
                                 for f in range(2)])
-        logit = SN.score_logit(weights, pts, df, grasp) if len(pts) else float("nan")
+        logit = SN.score_logit(weights, pts, df, grasp, net_dtype) if len(pts) else float("nan")
         J += np.inf if np.isnan(logit) else -100.0 * logit
         metric += r["metric"]
         poses.append(pose); fins.append(r["cur_pos"]); logits.append(logit); trace.append(r["poses"])

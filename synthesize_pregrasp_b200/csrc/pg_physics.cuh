@@ -779,6 +779,9 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
     // ---- friction pairs with the implicit cone
     for (int k = 0; k < rs.n_pts; k++) {
       PRow& r = rs.pt[k];
+      // no normal impulse and no stored friction impulse: the cone clips both rows to zero, nothing changes
+      // (identical result, zero residual) -- skip the row pair
+      if (r.impN == 0.0 && r.imp1 == 0.0 && r.imp2 == 0.0) continue;
       const int da = r.a - MAX_STATICS, db = r.b - MAX_STATICS;
       V3 l1 = r.l1, l2 = r.l2;
       V3 tA1 = cross(r.relA, l1), tB1 = cross(r.relB, -l1), tA2 = cross(r.relA, l2), tB2 = cross(r.relB, -l2);

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(RK_THREADS, 7) rollout_kernel(const EnvDev* __
   out.metric = metric ? metric + k : nullptr;
   out.trace = trace ? trace + (size_t)k * N * SKIP * 7 : nullptr;
   out.iters = iters ? iters + (size_t)k * N * SKIP : nullptr;
+  out.settle_iters = nullptr;
   rollout_one(*env, u, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path, max_force, 1, out, nullptr, 0);   // solver slice: dynamic shared memory, see PG_SM
 }
 

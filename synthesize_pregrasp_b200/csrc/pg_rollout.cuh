@@ -146,6 +146,7 @@ struct RolloutOut {
   double* metric;     // scalar
   double* trace;      // optional [N*SKIP][7]: pose at the START of every control substep (model_test.py:124-135)
   int* iters;         // optional [N*SKIP]
+  int* settle_iters;  // optional [settle_substeps] (host diagnostics only)
 };
 
 // sm / ss: the thread's on-chip solver slice (element i at sm[i*ss]); SM_DOUBLES elements
@@ -230,7 +231,10 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
     // ---- settle + metric :556-603 (train mode)
     if (j == N - 1 && train) {
       double m0 = (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
-      for (int s = 0; s < E.settle_substeps; s++) substep(E, S, statR, rs, sm, ss);
+      for (int s = 0; s < E.settle_substeps; s++) {
+        substep(E, S, statR, rs, sm, ss);
+        if (out.settle_iters) out.settle_iters[s] = S.last_iterations;
+      }
       if (out.metric) *out.metric = m0 + (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
     }
     DynBody& o = S.dyn[0];

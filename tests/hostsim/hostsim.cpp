@@ -4,6 +4,8 @@
 #include "../../synthesize_pregrasp_b200/csrc/pg_envbuild.h"
 #include "../../synthesize_pregrasp_b200/csrc/pg_rollout.cuh"
 
+static int* g_settle = nullptr;
+extern "C" void hostsim_set_settle_buffer(int* p) { g_settle = p; }
 extern "C" int hostsim_rollout(const PgEnvSpec* sp, const double* u, const float* noise, int K, int N, const int* path,
                                double max_force, int train, double* pose, double* fins, double* metric, double* trace,
                                int* iters) {
@@ -18,6 +20,7 @@ extern "C" int hostsim_rollout(const PgEnvSpec* sp, const double* u, const float
     out.metric = metric ? metric + k : nullptr;
     out.trace = trace ? trace + (size_t)k * N * 50 * 7 : nullptr;
     out.iters = iters ? iters + (size_t)k * N * 50 : nullptr;
+    out.settle_iters = g_settle ? g_settle + (size_t)k * 512 : nullptr;
     double sm[pg::SM_DOUBLES];
     pg::rollout_one(E, u, noise ? noise + (size_t)k * N * 48 : nullptr, N, path, max_force, train, out, sm, 1);
   }

@@ -237,3 +237,41 @@ def test_errors_are_reported_not_swallowed(EN):
     eng = EN.RolloutEngine(make_spec("foodbox"), device=0)
     with pytest.raises(RuntimeError):
         eng.rollout(np.zeros((2, 48)), None, [0, 7], 20.0, K=1)   # contact state out of range
+
+
+def test_ragged_and_edge_batches(EN):
+    """K not a multiple of the CTA size, K=1, N=1 and N=3: each rollout must equal the same rollout run alone."""
+    from synthesize_pregrasp_b200.envspec import make_spec
+    eng = EN.RolloutEngine(make_spec("keyboard"), device=0)
+    gen = torch.Generator(device="cuda:0").manual_seed(5)
+    for K, N in ((1, 2), (65, 1), (130, 3)):
+        noise = 0.8 * torch.randn((K, N, 48), generator=gen, device="cuda:0", dtype=torch.float32)
+        u = 0.1 * np.ones((N, 48))
+        J, metric = eng.rollout(u, noise, [0] * N, 20.0, want_metric=True)
+        assert J.shape == (K,) and torch.isfinite(J).all()
+        for k in (0, K - 1):
+            Jk, mk = eng.rollout(u, noise[k:k + 1].contiguous(), [0] * N, 20.0, want_metric=True)
+            assert float(Jk) == float(J[k]) and float(mk) == float(metric[k])      # batch position must not matter
+    # replay form (noise = NULL) equals zero noise
+    z = torch.zeros((1, 2, 48), device="cuda:0", dtype=torch.float32)
+    u = 0.3 * np.ones((2, 48))
+    assert float(eng.rollout(u, None, [0, 0], 20.0, K=1)) == float(eng.rollout(u, z, [0, 0], 20.0))
+
+
+def test_two_env_handles_on_two_streams(EN):
+    """BASELINE config 5: independent env handles run concurrently on their own streams."""
+    from synthesize_pregrasp_b200.envspec import make_spec
+    engs = [EN.RolloutEngine(make_spec(n), device=0) for n in ("foodbox", "keyboard")]
+    gen = torch.Generator(device="cuda:0").manual_seed(8)
+    noise = 0.8 * torch.randn((96, 2, 48), generator=gen, device="cuda:0", dtype=torch.float32)
+    u = np.zeros((2, 48))
+    ref = [e.rollout(u, noise, [0, 0], 20.0).clone() for e in engs]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in engs]
+    outs = []
+    for e, s in zip(engs, streams):
+        with torch.cuda.stream(s):
+            outs.append(e.rollout(u, noise, [0, 0], 20.0))
+    torch.cuda.synchronize()
+    for a, b in zip(ref, outs):
+        assert torch.equal(a, b)
