@@ -729,85 +729,131 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
   for (int c = 0; c < ncons; c++) max_imp[c] = S.cons[cval[c]].max_impulse;
   const double m_obj = 1.0 / S.dyn[0].mass, m_tip = 1.0 / S.dyn[1].mass;   // inverse masses
 
+  // Register-resident copies of one row, loaded one row AHEAD of their use (software pipelining): the row records
+  // live in thread-local memory (L1/L2), and an exposed L2 round trip per row was the top stall in the ncu source view.
+  struct NcRegs { double rhs, inv, den, imp, mi; V3 col; int d, i; };
+  struct NRegs { V3 relA, relB, n; double rhs, inv, den, imp; int da, db; };
+#if defined(__CUDA_ARCH__)
+#define PG_PIN(x) asm volatile("" : "+d"(x))
+#define PG_PIN3(v) { PG_PIN((v).x); PG_PIN((v).y); PG_PIN((v).z); }
+#else
+#define PG_PIN(x)
+#define PG_PIN3(v)
+#endif
+  const int nn = rs.nc.n;
+  const double mi0 = max_imp[0], mi1 = max_imp[1];
+  const int ncb0 = rs.nc.body[0], ncb1 = rs.nc.body[1];
+  auto load_nc = [&](int index) -> NcRegs {
+    NcRegs q;
+    int c = index >= 6 ? 1 : 0;
+    q.i = index - 6 * c; q.d = c ? ncb1 : ncb0; q.mi = c ? mi1 : mi0;
+    q.rhs = rs.nc.rhs[index]; q.inv = rs.nc.inv[index]; q.den = rs.nc.den[index]; q.imp = rs.nc.imp[index];
+    q.col = (q.i >= 3) ? rs.nc.col[c][q.i - 3] : V3();
+    PG_PIN(q.rhs); PG_PIN(q.inv); PG_PIN(q.den); PG_PIN(q.imp); PG_PIN3(q.col);
+    return q;
+  };
+  auto load_n = [&](int k) -> NRegs {
+    const PRow& r = rs.pt[k];
+    NRegs q;
+    q.relA = r.relA; q.relB = r.relB; q.n = r.n; q.rhs = r.rhsN; q.inv = r.invN; q.den = r.denN; q.imp = r.impN;
+    q.da = r.a - MAX_STATICS; q.db = r.b - MAX_STATICS;
+    PG_PIN3(q.relA); PG_PIN3(q.relB); PG_PIN3(q.n); PG_PIN(q.rhs); PG_PIN(q.inv); PG_PIN(q.den); PG_PIN(q.imp);
+    return q;
+  };
+
   int it;
   for (it = 0; it < E.iterations; it++) {
     double lsr = 0;
     // ---- fingertip servo rows, alternating sweep direction
-    const int nn = rs.nc.n;
-    for (int j = 0; j < nn; j++) {
-      int index = (it & 1) ? j : nn - 1 - j;
-      int c = index / 6, i = index - 6 * c, d = rs.nc.body[c];
-      double inv = rs.nc.inv[index], imp = rs.nc.imp[index], delta = rs.nc.rhs[index], mi = max_imp[c];
-      const double den = rs.nc.den[index];
-      if (i < 3) {
-        double a = 0;
-        a += PG_SM(SM_DV + 6 * d + 3 + i);            // jacobian = unit vector e_i on the linear part
-        delta -= a * inv;
-      } else {
-        V3 na = rs.nc.col[c][i - 3];
-        delta -= side_dot(sm, ss, d, na, V3()) * inv;
+    if (nn > 0) {
+      NcRegs cur = load_nc((it & 1) ? 0 : nn - 1);
+      for (int j = 0; j < nn; j++) {
+        const int index = (it & 1) ? j : nn - 1 - j;
+        NcRegs nxt = cur;
+        if (j + 1 < nn) nxt = load_nc((it & 1) ? j + 1 : nn - 2 - j);
+        const int d = cur.d, i = cur.i;
+        double delta = cur.rhs, imp = cur.imp;
+        if (i < 3) {
+          double a = 0;
+          a += PG_SM(SM_DV + 6 * d + 3 + i);            // jacobian = unit vector e_i on the linear part
+          delta -= a * cur.inv;
+        } else {
+          delta -= side_dot(sm, ss, d, cur.col, V3()) * cur.inv;
+        }
+        double sum = imp + delta;
+        if (sum < -cur.mi) { delta = -cur.mi - imp; imp = -cur.mi; }
+        else if (sum > cur.mi) { delta = cur.mi - imp; imp = cur.mi; }
+        else imp = sum;
+        rs.nc.imp[index] = imp;
+        if (i < 3) PG_SM(SM_DV + 6 * d + 3 + i) += m_tip * delta;
+        else side_apply(sm, ss, d, cur.col, V3(), m_tip, delta);
+        double res = delta * cur.den;            // = delta / inv, the velocity change of this row
+        lsr = fmax(lsr, res * res);
+        cur = nxt;
       }
-      double sum = imp + delta;
-      if (sum < -mi) { delta = -mi - imp; imp = -mi; }
-      else if (sum > mi) { delta = mi - imp; imp = mi; }
-      else imp = sum;
-      rs.nc.imp[index] = imp;
-      if (i < 3) PG_SM(SM_DV + 6 * d + 3 + i) += m_tip * delta;
-      else side_apply(sm, ss, d, rs.nc.col[c][i - 3], V3(), m_tip, delta);
-      double res = delta * den;            // = delta / inv, the velocity change of this row
-      lsr = fmax(lsr, res * res);
     }
     // ---- normal rows
-    for (int k = 0; k < rs.n_pts; k++) {
-      PRow& r = rs.pt[k];
-      const int da = r.a - MAX_STATICS, db = r.b - MAX_STATICS;
-      V3 n = r.n, tA = cross(r.relA, n), tB = cross(r.relB, -n);
-      double delta = r.rhsN, a = 0, b = 0;
-      if (da >= 0) a = side_dot(sm, ss, da, tA, n);
-      if (db >= 0) b = side_dot(sm, ss, db, tB, -n);
-      delta -= a * r.invN;
-      delta -= b * r.invN;
-      double sum = r.impN + delta;
-      if (sum < 0.0) { delta = 0.0 - r.impN; r.impN = 0.0; }
-      else if (sum > 1e10) { delta = 1e10 - r.impN; r.impN = 1e10; }
-      else r.impN = sum;
-      if (da >= 0) side_apply(sm, ss, da, tA, n, da == 0 ? m_obj : m_tip, delta);
-      if (db >= 0) side_apply(sm, ss, db, tB, -n, db == 0 ? m_obj : m_tip, delta);
-      double res = delta * r.denN;
-      lsr = fmax(lsr, res * res);
+    if (rs.n_pts > 0) {
+      NRegs cur = load_n(0);
+      for (int k = 0; k < rs.n_pts; k++) {
+        NRegs nxt = cur;
+        if (k + 1 < rs.n_pts) nxt = load_n(k + 1);
+        const int da = cur.da, db = cur.db;
+        V3 n = cur.n, tA = cross(cur.relA, n), tB = cross(cur.relB, -n);
+        double delta = cur.rhs, a = 0, b = 0;
+        if (da >= 0) a = side_dot(sm, ss, da, tA, n);
+        if (db >= 0) b = side_dot(sm, ss, db, tB, -n);
+        delta -= a * cur.inv;
+        delta -= b * cur.inv;
+        double sum = cur.imp + delta, impn;
+        if (sum < 0.0) { delta = 0.0 - cur.imp; impn = 0.0; }
+        else if (sum > 1e10) { delta = 1e10 - cur.imp; impn = 1e10; }
+        else impn = sum;
+        rs.pt[k].impN = impn;
+        if (da >= 0) side_apply(sm, ss, da, tA, n, da == 0 ? m_obj : m_tip, delta);
+        if (db >= 0) side_apply(sm, ss, db, tB, -n, db == 0 ? m_obj : m_tip, delta);
+        double res = delta * cur.den;
+        lsr = fmax(lsr, res * res);
+        cur = nxt;
+      }
     }
     // ---- friction pairs with the implicit cone
     for (int k = 0; k < rs.n_pts; k++) {
       PRow& r = rs.pt[k];
       // no normal impulse and no stored friction impulse: the cone clips both rows to zero, nothing changes
       // (identical result, zero residual) -- skip the row pair
-      if (r.impN == 0.0 && r.imp1 == 0.0 && r.imp2 == 0.0) continue;
+      const double impN = r.impN, imp1 = r.imp1, imp2 = r.imp2;
+      if (impN == 0.0 && imp1 == 0.0 && imp2 == 0.0) continue;
       const int da = r.a - MAX_STATICS, db = r.b - MAX_STATICS;
-      V3 l1 = r.l1, l2 = r.l2;
-      V3 tA1 = cross(r.relA, l1), tB1 = cross(r.relB, -l1), tA2 = cross(r.relA, l2), tB2 = cross(r.relB, -l2);
-      double lim = r.mu * r.impN, lo = -lim;
-      double dB = r.rhs2, dA = r.rhs1, a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+      V3 l1 = r.l1, l2 = r.l2, relA = r.relA, relB = r.relB;
+      double inv1 = r.inv1, inv2 = r.inv2, den1 = r.den1, den2 = r.den2, rhs1 = r.rhs1, rhs2 = r.rhs2, mu = r.mu;
+      PG_PIN3(l1); PG_PIN3(l2); PG_PIN3(relA); PG_PIN3(relB);
+      PG_PIN(inv1); PG_PIN(inv2); PG_PIN(den1); PG_PIN(den2); PG_PIN(rhs1); PG_PIN(rhs2); PG_PIN(mu);
+      V3 tA1 = cross(relA, l1), tB1 = cross(relB, -l1), tA2 = cross(relA, l2), tB2 = cross(relB, -l2);
+      double lim = mu * impN, lo = -lim;
+      double dB = rhs2, dA = rhs1, a1 = 0, b1 = 0, a2 = 0, b2 = 0;
       if (da >= 0) { a2 = side_dot(sm, ss, da, tA2, l2); a1 = side_dot(sm, ss, da, tA1, l1); }
       if (db >= 0) { b2 = side_dot(sm, ss, db, tB2, -l2); b1 = side_dot(sm, ss, db, tB1, -l1); }
-      dB -= a2 * r.inv2; dB -= b2 * r.inv2;
-      dA -= a1 * r.inv1; dA -= b1 * r.inv1;
-      double sumB = r.imp2 + dB, sumA = r.imp1 + dA;
+      dB -= a2 * inv2; dB -= b2 * inv2;
+      dA -= a1 * inv1; dA -= b1 * inv1;
+      double sumB = imp2 + dB, sumA = imp1 + dA, o1, o2;
       if (sumA * sumA + sumB * sumB >= lo * lo) {
         // |lo*sin(atan2(a,b))| = |lo*a|/hypot, |lo*cos(atan2(a,b))| = |lo*b|/hypot: same clip without transcendentals
         double rinv = 1.0 / sqrt(sumA * sumA + sumB * sumB);
         double ca = fabs(lo * sumA * rinv), cb = fabs(lo * sumB * rinv);
-        if (sumA < -ca) { dA = -ca - r.imp1; r.imp1 = -ca; }
-        else if (sumA > ca) { dA = ca - r.imp1; r.imp1 = ca; }
-        else r.imp1 = sumA;
-        if (sumB < -cb) { dB = -cb - r.imp2; r.imp2 = -cb; }
-        else if (sumB > cb) { dB = cb - r.imp2; r.imp2 = cb; }
-        else r.imp2 = sumB;
-      } else { r.imp1 = sumA; r.imp2 = sumB; }
+        if (sumA < -ca) { dA = -ca - imp1; o1 = -ca; }
+        else if (sumA > ca) { dA = ca - imp1; o1 = ca; }
+        else o1 = sumA;
+        if (sumB < -cb) { dB = -cb - imp2; o2 = -cb; }
+        else if (sumB > cb) { dB = cb - imp2; o2 = cb; }
+        else o2 = sumB;
+      } else { o1 = sumA; o2 = sumB; }
+      r.imp1 = o1; r.imp2 = o2;
       // both deltas were computed against the same velocities (Jacobi inside the pair), so the two impulses of a
       // body are applied as ONE combined linear + angular impulse (one inverse-inertia product per body)
       if (da >= 0) side_apply2(sm, ss, da, tA1 * dA + tA2 * dB, l1 * dA + l2 * dB, da == 0 ? m_obj : m_tip);
       if (db >= 0) side_apply2(sm, ss, db, tB1 * dA + tB2 * dB, -(l1 * dA + l2 * dB), db == 0 ? m_obj : m_tip);
-      double res = dA * r.den1 + dB * r.den2;
+      double res = dA * den1 + dB * den2;
       lsr = fmax(lsr, res * res);
     }
     if (lsr <= E.residual_threshold || it >= E.iterations - 1) { it++; break; }
