@@ -4,7 +4,8 @@ simple_check_*: restates utils/dyn_feasibility_check.py:124-235 (project2norm, c
 `c1<0 and c1<0` typo, check_sign_change, simple_check_dyn_feasible_3p, simple_check_dyn_feasible); the two
 pytorch_kinematics calls at :191-196 (axis_angle_to_quaternion, quaternion_apply) are restated from their
 published definitions (pytorch3d transforms) in float64.
-qp_*: restates the QP of :28-60 / :79-112 / :239-303 -- PARITY UNPINNED (cvxpy/OSQP absent, nothing recorded).
+qp_matrices: the QP data of :28-60 / :93-101 (Q, G, h and the 6x9 wrench map).  The QP SOLVE is not restated: its
+optimum is PARITY UNPINNED (cvxpy/OSQP absent, nothing recorded) and no kernel is shipped for it this round.
 """
 import itertools
 
@@ -129,38 +130,3 @@ def qp_matrices(p, nrm_unit_or_raw, mu=MU, normalise=True):
     h = np.hstack([np.zeros(12), -np.ones(3)]) * MIN_NORMAL_FORCE_3
     W = np.hstack([A1, A2]).T                                   # 6x9 wrench map, Q = W^T W
     return Q, G, h, W
-
-
-def qp_optimum(p, nrm, normalise=True, iters=200):
-    """min 1/2 z'Qz s.t. Gz<=h, solved exactly by a primal active-set method on the regularised Hessian
-    (Q + 1e-12 I keeps the KKT systems non-singular; Q has rank <= 6)."""
-    Q, G, h, _ = qp_matrices(np.asarray(p, np.float64), np.asarray(nrm, np.float64), normalise=normalise)
-    H = Q + 1e-12 * np.eye(9)
-    # feasible start: z_n = -1 for each finger, tangentials 0  (mu*z_n +- z_t <= 0 holds since z_n<0)
-    z = np.zeros(9)
-    z[0::3] = -1.0
-    active = [12, 13, 14]
-    for _ in range(iters):
-        A = G[active] if active else np.zeros((0, 9))
-        m = len(active)
-        K = np.block([[H, A.T], [A, np.zeros((m, m))]])
-        rhs = np.concatenate([-H @ z, np.zeros(m)])
-        sol = np.linalg.lstsq(K, rhs, rcond=None)[0]
-        d, lam = sol[:9], sol[9:]
-        if np.linalg.norm(d) < 1e-12:
-            if m == 0 or lam.min() >= -1e-12:
-                break
-            active.pop(int(np.argmin(lam)))
-            continue
-        Gd = G @ d
-        slack = h - G @ z
-        step, block = 1.0, -1
-        for i in range(15):
-            if i not in active and Gd[i] > 1e-14:
-                t = slack[i] / Gd[i]
-                if t < step:
-                    step, block = t, i
-        z = z + step * d
-        if block >= 0:
-            active.append(block)
-    return 0.5 * float(z @ Q @ z), z

@@ -116,13 +116,16 @@ class EnvSim:
         self.close()
         self.h = self.L.pgo_create()
         for k, v in self.params.items():
+            if k == "obj_compound":
+                continue
             self.L.pgo_set_param(self.h, k.encode(), float(v))
         self.static_ids = {}
         names = s["static_names"]
         for name in s["order"]:
             if name == "obj":
                 self.obj = self._add(s["obj_shape"], s["obj_half"], s.get("obj_hull"), s["obj_mass"], s["obj_pos"],
-                                     s["obj_quat"], s["obj_friction"])
+                                     s["obj_quat"], s["obj_friction"],
+                                     compound=bool(self.params.get("obj_compound", s["obj_shape"] == 1)))
             else:
                 half, pos, quat, fr = s["statics"][names.index(name)]
                 self.static_ids[name] = self._add(0, half, None, 0.0, pos, quat, fr, compound=(name == "floor"))

@@ -127,6 +127,8 @@ struct Body {
   bool compound = false;  // floor: btCompoundShape wrapper => always body A of its pairs
   M3 R;            // cached rotation
   V3 aabb_lo, aabb_hi;
+  V3 proxy_lo, proxy_hi;   // tight AABB the broadphase proxy was (re)created with
+  bool early = false;      // tips: the re-created object proxy found this tip at creation (tight AABBs overlapping)
 };
 
 struct ManifoldPoint {
@@ -169,6 +171,8 @@ struct Params {
   double breaking_factor = 0.02;  // gContactBreakingThreshold
   double aabb_margin = 0.02;      // contact threshold added to AABBs
   double max_coord_vel = 100.0;   // btMultiBody::m_maxCoordinateVelocity
+  int pair_order_mode = -1;       // -1: by object type; 0: box-object order; 1: compound-object order (see collide)
+  int manifold_order3 = 0;        // debugging: explicit order (digits, creation indices) when exactly 3 manifolds are solved
   int manifold_order = 0;         // 0: emulate quickSort of dispatcher order; k>=1: (k-1)-th permutation of creation order
   int constraint_reverse = 1;     // [H] quickSort of equal island ids reverses the two servo constraints
   int residual_max = 1;           // 1: max over rows, 0: sum
@@ -231,6 +235,7 @@ static void compute_aabb(Body& b, double extra) {
   b.aabb_hi = wc + we + V3(extra, extra, extra);
 }
 
+static double g_hull_inertia_pad = 0.002;   // [H] see shape_inertia
 static V3 shape_inertia(const Shape& s, double mass) {
   double lx, ly, lz;
   if (s.type == SH_BOX) { lx = 2 * s.half.x; ly = 2 * s.half.y; lz = 2 * s.half.z; }
@@ -240,8 +245,10 @@ static V3 shape_inertia(const Shape& s, double mass) {
     double t1 = mass / 12.0 * h2 + mass / 4.0 * r2, t2 = mass / 2.0 * r2;
     return V3(t1, t1, t2);
   } else {
-    // btCompoundShape / btPolyhedralConvexShape: box inertia of the (margin-inclusive) local AABB
+    // btCompoundShape::calculateLocalInertia: box inertia of the compound's AABB.  The cached hull AABB carries the
+    // margin three times (support with margin + recalcLocalAabb + btTransformAabb) and the compound adds its own
     V3 c, e; local_aabb(s, c, e);
+    e = e + V3(g_hull_inertia_pad, g_hull_inertia_pad, g_hull_inertia_pad);
     lx = 2 * e.x; ly = 2 * e.y; lz = 2 * e.z;
   }
   return V3(mass / 12.0 * (ly * ly + lz * lz), mass / 12.0 * (lx * lx + lz * lz), mass / 12.0 * (lx * lx + ly * ly));
@@ -623,7 +630,28 @@ static void destroy_manifolds_of(World& w, int body) {
 // their pairs and manifolds dropped)
 static void refresh_proxy(World& w, int body) {
   destroy_manifolds_of(w, body);
-  w.bodies[body].uid = w.next_uid++;
+  Body& b = w.bodies[body];
+  b.uid = w.next_uid++;
+  // btDbvtBroadphase::createProxy collides the NEW proxy's tight AABB against both trees at once (no deferred
+  // collide): pairs found here enter the pair cache before the ones the next updateAabbs finds with fat AABBs
+  update_cache(b); compute_aabb(b, 0.0);
+  b.proxy_lo = b.aabb_lo; b.proxy_hi = b.aabb_hi;
+  if (body == w.obj) {
+    double depth[2] = {-1, -1};
+    for (int t = 0; t < 2; t++) if (w.tip[t] >= 0) {
+      Body& tb = w.bodies[w.tip[t]];
+      double d = 1e300;                       // smallest per-axis overlap of the two tight AABBs (< 0: separated)
+      for (int k = 0; k < 3; k++) d = std::min(d, std::min(tb.proxy_hi[k] - b.proxy_lo[k], b.proxy_hi[k] - tb.proxy_lo[k]));
+      depth[t] = filter_disabled(w, body, w.tip[t]) ? -1.0 : d;
+    }
+    for (int t = 0; t < 2; t++) if (w.tip[t] >= 0) {
+      // [H] a tip that merely touches the object (overlap below 1e-6: placed exactly on a face) is found at creation
+      // only when it is the single active tip; with the other tip clearly overlapping it enters the cache later
+      bool marginal = depth[t] < 1e-6, other_clear = depth[1 - t] >= 1e-6;
+      w.bodies[w.tip[t]].early = depth[t] >= 0 && !(marginal && other_clear);
+      if (w.P.debug == 1) fprintf(stderr, "refresh obj: tip %d overlap %.3g early %d\n", t, depth[t], (int)w.bodies[w.tip[t]].early);
+    }
+  }
 }
 
 static void set_collision_filter(World& w, int a, int b, bool enable) {
@@ -667,11 +695,30 @@ static void collide(World& w) {
   // index tip, then the walls; pairs that do not involve the object come last.
   std::vector<std::pair<int, int>> cand;
   auto push = [&](int i, int j) { if (i >= 0 && j >= 0 && i != j) cand.push_back({std::min(i, j), std::max(i, j)}); };
-  if (w.obj >= 0) {
+  int mode = w.P.pair_order_mode;
+  if (mode < 0) mode = 1;
+  if (w.obj >= 0 && mode == 0) {
     push(w.obj, w.tip[0]);
     for (int i = 0; i < nb; i++) if (w.bodies[i].compound) push(w.obj, i);
     push(w.obj, w.tip[1]);
     for (int i = 0; i < nb; i++) if (w.bodies[i].is_static && !w.bodies[i].compound) push(w.obj, i);
+  } else if (w.obj >= 0) {
+    // pair-cache order after PyBullet's setCollisionFilterPair sequence (every call re-creates both proxies): the
+    // surviving tip-tip / wall-tip pairs, then what the re-created object proxy found at creation -- dynamic tree
+    // first (index tip, thumb: only tips whose tight AABB overlapped), then the static tree -- then the tip pairs
+    // the first updateAabbs finds with fat AABBs.  Tree traversal orders are fitted to the recorded trajectories.
+    bool tt_early = false;
+    if (w.tip[0] >= 0 && w.tip[1] >= 0) {
+      const Body& a = w.bodies[w.tip[0]]; const Body& b = w.bodies[w.tip[1]];
+      tt_early = true;
+      for (int k = 0; k < 3; k++) if (a.proxy_lo[k] > b.proxy_hi[k] || a.proxy_hi[k] < b.proxy_lo[k]) tt_early = false;
+    }
+    if (tt_early) push(w.tip[0], w.tip[1]);
+    for (int i = 0; i < nb; i++) if (w.bodies[i].is_static && !w.bodies[i].compound) { push(i, w.tip[1]); push(i, w.tip[0]); }
+    for (int t = 1; t >= 0; t--) if (w.tip[t] >= 0 && w.bodies[w.tip[t]].early) push(w.obj, w.tip[t]);
+    for (int i = 0; i < nb; i++) if (w.bodies[i].compound && i != w.obj) push(w.obj, i);
+    for (int i = 0; i < nb; i++) if (w.bodies[i].is_static && !w.bodies[i].compound) push(w.obj, i);
+    for (int t = 1; t >= 0; t--) if (w.tip[t] >= 0 && !w.bodies[w.tip[t]].early) push(w.obj, w.tip[t]);
   }
   for (int i = 0; i < nb; i++) for (int j = i + 1; j < nb; j++) {
     bool seen = false;
@@ -921,7 +968,12 @@ static void solve(World& w) {
   for (int isl : islands) {
     std::vector<int> mlist;
     for (auto& o : order) if (o.first == isl || isl == -2) mlist.push_back(o.second);
-    if (P.manifold_order >= 10000 && mlist.size() > 1) {
+    int nd3 = 0; for (int c = P.manifold_order3; c > 0; c /= 10) nd3++;
+    if (P.manifold_order3 > 0 && (int)mlist.size() == nd3 - 1) {
+      std::sort(mlist.begin(), mlist.end());
+      std::vector<int> src = mlist; int code = P.manifold_order3;
+      for (int k = nd3 - 2; k >= 0; k--) { mlist[k] = src[code % 10]; code /= 10; }
+    } else if (P.manifold_order >= 10000 && mlist.size() > 1) {
       // explicit order: digits of (manifold_order - 10000), zero padded to mlist.size(), index creation order
       std::sort(mlist.begin(), mlist.end());
       std::vector<int> src = mlist; int code = P.manifold_order - 10000; int n = (int)src.size();
@@ -930,6 +982,7 @@ static void solve(World& w) {
       std::sort(mlist.begin(), mlist.end());
       for (int k = 0; k < P.manifold_order - 1; k++) std::next_permutation(mlist.begin(), mlist.end());
     }
+    if (P.debug == 1) { fprintf(stderr, "step %d solve order:", w.step_count); for (int mi : mlist) fprintf(stderr, " [%d](%d-%d n%d)", mi, w.manifolds[mi].a, w.manifolds[mi].b, w.manifolds[mi].n); fprintf(stderr, "\n"); }
     std::vector<SolverRow> nc, normal, fric;
     w.dv.assign(6 * nb, 0.0);
     w.ws.assign(6 * nb, 0.0);
@@ -1070,8 +1123,11 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin)
-  S(max_coord_vel) S(manifold_order) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(default_max_impulse) S(debug)
 #undef S
+  if (!strcmp(name, "hull_inertia_pad")) { g_hull_inertia_pad = v; return; }
+  if (!strcmp(name, "pen_tie")) { g_pen_tie = v; return; }
+  if (!strcmp(name, "epa_variant")) { epa2::g_epa_variant = (int)v; return; }
   fprintf(stderr, "pgo_set_param: unknown %s\n", name);
 }
 

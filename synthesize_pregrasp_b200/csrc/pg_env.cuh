@@ -25,6 +25,7 @@ struct EnvDev {
   int obj_shape, n_hull;
   double obj_half[3], obj_mass, obj_inertia[3], obj_pos[3], obj_quat[4], obj_friction, obj_margin, obj_radius_bs;
   double hull[MAX_HULL * 3];
+  double obj_aabb_c[3], obj_aabb_e[3];   // local AABB centre / half extent (margin included) of the object shape
   // static scene
   int n_static, floor_index;
   BoxBody statics[MAX_STATICS];

@@ -12,7 +12,8 @@ namespace pg {
 static inline double box_radius(const double* h) { return sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]); }
 
 static inline int build_envdev(const PgEnvSpec* sp, EnvDev& E, std::string& err) {
-  if (sp->obj_shape != SHAPE_BOX) { err = "only box objects are built in this round (hull/cylinder: GJK path pending)"; return PG_ERR_UNSUPPORTED; }
+  if (sp->obj_shape != SHAPE_BOX && sp->obj_shape != SHAPE_HULL) { err = "cylinder objects (waterbottle) are not built in this round"; return PG_ERR_UNSUPPORTED; }
+  if (sp->obj_shape == SHAPE_HULL && (sp->n_hull < 4 || sp->n_hull > MAX_HULL || !sp->hull)) { err = "hull needs 4..64 vertices"; return PG_ERR_INVALID; }
   if (sp->n_static < 1 || sp->n_static > MAX_STATICS || sp->n_regions > MAX_REGIONS || sp->n_states > MAX_STATES || !sp->csg) {
     err = "spec out of supported bounds"; return PG_ERR_INVALID;
   }
@@ -25,10 +26,31 @@ static inline int build_envdev(const PgEnvSpec* sp, EnvDev& E, std::string& err)
   for (int i = 0; i < 3; i++) { E.obj_half[i] = sp->obj_half[i]; E.obj_pos[i] = sp->obj_pos[i]; }
   for (int i = 0; i < 4; i++) E.obj_quat[i] = sp->obj_quat[i];
   E.obj_mass = sp->obj_mass; E.obj_friction = sp->obj_friction; E.obj_margin = 0.001;
-  {
+  if (sp->obj_shape == SHAPE_BOX) {
     double lx = 2 * E.obj_half[0], ly = 2 * E.obj_half[1], lz = 2 * E.obj_half[2], m = E.obj_mass;   // btBoxShape::calculateLocalInertia
     E.obj_inertia[0] = m / 12.0 * (ly * ly + lz * lz); E.obj_inertia[1] = m / 12.0 * (lx * lx + lz * lz); E.obj_inertia[2] = m / 12.0 * (lx * lx + ly * ly);
     E.obj_radius_bs = box_radius(E.obj_half);
+    for (int i = 0; i < 3; i++) { E.obj_aabb_c[i] = 0; E.obj_aabb_e[i] = E.obj_half[i]; }
+  } else {
+    // URDF mesh -> btCompoundShape(btConvexHullShape): inertia = box inertia of the compound's AABB, which carries the
+    // margin three times (recorded plate trajectory: pad 0.003 over the vertex extents); bounding sphere from the
+    // margin-inclusive AABB
+    E.n_hull = sp->n_hull;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int v = 0; v < sp->n_hull; v++) for (int i = 0; i < 3; i++) {
+      double x = sp->hull[3 * v + i]; E.hull[3 * v + i] = x;
+      if (x < lo[i]) lo[i] = x;
+      if (x > hi[i]) hi[i] = x;
+    }
+    double l[3], r2 = 0, c2 = 0;
+    for (int i = 0; i < 3; i++) {
+      E.obj_aabb_c[i] = 0.5 * (hi[i] + lo[i]); E.obj_aabb_e[i] = 0.5 * (hi[i] - lo[i]) + E.obj_margin;
+      l[i] = 2 * (E.obj_aabb_e[i] + 0.002);
+      r2 += E.obj_aabb_e[i] * E.obj_aabb_e[i]; c2 += E.obj_aabb_c[i] * E.obj_aabb_c[i];
+    }
+    double m = E.obj_mass;
+    E.obj_inertia[0] = m / 12.0 * (l[1] * l[1] + l[2] * l[2]); E.obj_inertia[1] = m / 12.0 * (l[0] * l[0] + l[2] * l[2]); E.obj_inertia[2] = m / 12.0 * (l[0] * l[0] + l[1] * l[1]);
+    E.obj_radius_bs = sqrt(r2) + sqrt(c2);
   }
   E.n_static = sp->n_static; E.floor_index = sp->floor_index;
   for (int s = 0; s < sp->n_static; s++) {

@@ -167,6 +167,21 @@ def _prim_cloud(env):
     return c[env + "__points"], c[env + "__normals"]
 
 
+def bullet_hull_vertices(obj_vertices: np.ndarray) -> np.ndarray:
+    """Vertices of the convex hull PyBullet actually collides with for a URDF mesh (plate_contact_graph_env.py:198).
+
+    The OBJ loader keeps float32 coordinates and the URDF importer runs btConvexHullShape::optimizeConvexHull, whose
+    btConvexHullComputer snaps every point to a per-axis integer grid of extent/10216 (truncating toward the centre
+    of the bounding box) and returns the snapped coordinates.  The recorded plate trajectory is reproduced to 1e-15
+    over the settling phase only with these snapped vertices (3.3e-8 with the raw OBJ numbers).
+    """
+    v = np.asarray(obj_vertices, np.float64).astype(np.float32).astype(np.float64)
+    lo, hi = v.min(0), v.max(0)
+    s = (hi - lo) / 10216.0
+    c = (lo + hi) * 0.5
+    return np.trunc((v - c) * (1.0 / s)) * s + c
+
+
 def make_spec(env: str) -> EnvSpec:
     env = {"wallbox": "laptop"}.get(env, env)   # model_optimize.py:25 registers the laptop env as "wallbox"
     floor_dist = _o3d_box(2, 2, 0.02, (-1, -1, -0.02))
@@ -174,7 +189,7 @@ def make_spec(env: str) -> EnvSpec:
         a = _load("plate.npz")
         dummy, csg, paths = _states("plate")
         return EnvSpec(
-            name="plate", obj_shape=SHAPE_HULL, obj_half=(0.0, 0.0, 0.0), obj_hull=a["hull_vertices"],
+            name="plate", obj_shape=SHAPE_HULL, obj_half=(0.0, 0.0, 0.0), obj_hull=bullet_hull_vertices(a["hull_vertices"]),
             obj_mass=4.0,                                              # assets/plate_cvx_simple.urdf
             obj_pos=(0.0, 0.0, 0.0), obj_quat=_ID,                     # plate_env:192-199
             obj_friction=100.0,                                        # plate_env:210
