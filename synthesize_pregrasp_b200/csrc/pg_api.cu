@@ -46,7 +46,6 @@ struct Blob {
 
 extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   if (!sp || !out) { set_error("pg_env_create: null argument"); return PG_ERR_INVALID; }
-  if (sp->obj_shape != SHAPE_BOX) { set_error("pg_env_create: only box objects are built in this round (hull/cylinder: GJK path pending)"); return PG_ERR_UNSUPPORTED; }
   if (sp->n_static < 1 || sp->n_static > MAX_STATICS || sp->n_regions > MAX_REGIONS || sp->n_states > MAX_STATES ||
       sp->n_cloud != P_CLOUD || sp->n_crop < 1 || sp->n_crop > 2 || sp->n_dist_box > 4 || !sp->cloud || !sp->csg) {
     set_error("pg_env_create: spec out of supported bounds"); return PG_ERR_INVALID;

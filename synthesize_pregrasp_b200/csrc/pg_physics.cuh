@@ -11,6 +11,7 @@
 // orientation update, dt = 1/250 s.  fp64 throughout: contact-rich rollouts amplify rounding.
 #pragma once
 #include "pg_env.cuh"
+#include "pg_convex.cuh"
 #ifndef PG_BLOCK_THREADS
 #define PG_BLOCK_THREADS 64
 #endif
@@ -55,6 +56,8 @@ struct Sim {
   int nman;
   FixedCons cons[2];
   unsigned filter_off;   // bit i: tip i <-> object collision disabled
+  unsigned early;        // bit i: the re-created object proxy found tip i at creation (tight AABBs overlapping)
+  V3 plo[2], phi[2];     // tight AABB each tip's broadphase proxy was last (re)created with
   int obj_first;         // reset substep: object proxy is older than the walls'
   int last_iterations;
 };
@@ -396,22 +399,35 @@ PG_HD bool pair_allowed(const EnvDev& E, const Sim& S, int i, int j) {   // i < 
   return true;
 }
 
+// tight world AABB of a body's collision shape (hull objects: local AABB of the vertex cloud + margin)
+template <int SHAPE>
+PG_HD void tight_aabb(const EnvDev& E, const BodyView& b, int body, V3& lo, V3& hi) {
+  if (SHAPE == SHAPE_HULL && body == B_OBJ) {
+    V3 c(E.obj_aabb_c[0], E.obj_aabb_c[1], E.obj_aabb_c[2]), e(E.obj_aabb_e[0], E.obj_aabb_e[1], E.obj_aabb_e[2]);
+    V3 wc = mul(b.R, c) + b.pos, we;
+    for (int i = 0; i < 3; i++) we[i] = fabs(b.R(i, 0)) * e.x + fabs(b.R(i, 1)) * e.y + fabs(b.R(i, 2)) * e.z;
+    lo = wc - we; hi = wc + we;
+  } else aabb_of(b, 0.0, lo, hi);
+}
+
+template <int SHAPE>
 PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
   BodyView bv[NBODY];
   V3 lo[NBODY], hi[NBODY];
+  const double am = E.aabb_margin;
   for (int d = 0; d < 3; d++) S.dyn[d].R = qmat(S.dyn[d].q);
   for (int b = 0; b < NBODY; b++) {
     if (is_static(b) && b >= E.n_static) continue;
     bv[b] = view(E, S, statR, b);
-    aabb_of(bv[b], E.aabb_margin, lo[b], hi[b]);
+    tight_aabb<SHAPE>(E, bv[b], b, lo[b], hi[b]);
+    lo[b] = lo[b] - V3(am, am, am); hi[b] = hi[b] + V3(am, am, am);
   }
+  auto is_compound = [&](int b) -> bool { return is_static(b) ? (E.statics[b].compound != 0) : (SHAPE == SHAPE_HULL && b == B_OBJ); };
   auto pair_overlap = [&](int a, int b) -> bool {
     if (!overlap(lo[a], hi[a], lo[b], hi[b])) return false;
-    bool comp = (is_static(a) && E.statics[a].compound) || (is_static(b) && E.statics[b].compound);
-    if (comp) {   // btCompoundCollisionAlgorithm: child manifold lives only while the TIGHT aabbs overlap
-      double e = E.aabb_margin;
+    if (is_compound(a) || is_compound(b)) {   // btCompound(Compound)CollisionAlgorithm: child manifold lives only while the TIGHT aabbs overlap
       for (int k = 0; k < 3; k++)
-        if (lo[a][k] + e > hi[b][k] - e || hi[a][k] - e < lo[b][k] + e) return false;
+        if (lo[a][k] + am > hi[b][k] - am || hi[a][k] - am < lo[b][k] + am) return false;
     }
     return true;
   };
@@ -421,15 +437,20 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
     if (!pair_overlap(m.a, m.b)) { if (i != S.nman - 1) S.man[i] = S.man[S.nman - 1]; S.nman--; }
     else i++;
   }
-  // new manifolds in the order the broadphase reports the object's pairs: thumb, floor, index tip, walls,
-  // then wall-tip pairs and tip-tip (DESIGN.md "Row order")
-  int ca[MAXM + 4], cb[MAXM + 4], nc = 0;
-  ca[nc] = B_OBJ; cb[nc++] = B_TIP0;
-  ca[nc] = E.floor_index; cb[nc++] = B_OBJ;
-  ca[nc] = B_OBJ; cb[nc++] = B_TIP1;
-  for (int s = 0; s < E.n_static; s++) if (s != E.floor_index) { ca[nc] = s; cb[nc++] = B_OBJ; }
-  for (int s = 0; s < E.n_static; s++) if (s != E.floor_index) { ca[nc] = s; cb[nc++] = B_TIP0; ca[nc] = s; cb[nc++] = B_TIP1; }
-  ca[nc] = B_TIP0; cb[nc++] = B_TIP1;
+  // New manifolds are created in broadphase pair-cache order.  After PyBullet's setCollisionFilterPair sequence
+  // (every call re-creates both proxies) the cache holds: the surviving tip-tip and wall-tip pairs, then what the
+  // re-created object proxy found at creation -- dynamic tree (index tip, thumb; only tips whose tight AABB
+  // overlapped the object's), then the static tree -- then the tip pairs found with fat AABBs (DESIGN.md "Row order").
+  int ca[MAXM + 6], cb[MAXM + 6], nc = 0;
+  bool tt_early = true;
+  for (int k = 0; k < 3; k++) if (S.plo[0][k] > S.phi[1][k] || S.phi[0][k] < S.plo[1][k]) tt_early = false;
+  if (tt_early) { ca[nc] = B_TIP0; cb[nc++] = B_TIP1; }
+  for (int s = 0; s < E.n_static; s++) if (!E.statics[s].compound) { ca[nc] = s; cb[nc++] = B_TIP1; ca[nc] = s; cb[nc++] = B_TIP0; }
+  for (int t = 1; t >= 0; t--) if ((S.early >> t) & 1u) { ca[nc] = B_OBJ; cb[nc++] = B_TIP0 + t; }
+  for (int s = 0; s < E.n_static; s++) if (E.statics[s].compound) { ca[nc] = s; cb[nc++] = B_OBJ; }
+  for (int s = 0; s < E.n_static; s++) if (!E.statics[s].compound) { ca[nc] = s; cb[nc++] = B_OBJ; }
+  for (int t = 1; t >= 0; t--) if (!((S.early >> t) & 1u)) { ca[nc] = B_OBJ; cb[nc++] = B_TIP0 + t; }
+  if (!tt_early) { ca[nc] = B_TIP0; cb[nc++] = B_TIP1; }
   for (int c = 0; c < nc; c++) {
     int i = ca[c] < cb[c] ? ca[c] : cb[c], j = ca[c] < cb[c] ? cb[c] : ca[c];
     if (!pair_allowed(E, S, i, j)) continue;
@@ -439,11 +460,11 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
     if (have || S.nman >= MAXM) continue;
     Manifold& m = S.man[S.nman++];
     m.n = 0;
-    // body A: the compound floor always; otherwise the older broadphase proxy.  After the first
-    // pre_simulate the object's proxy is the youngest, so it is body B of every pair.
-    if (is_static(i) && !E.statics[i].compound && j == B_OBJ && S.obj_first) { m.a = (short)j; m.b = (short)i; }
+    // body A: a compound shape always (floor; hull object), otherwise the older broadphase proxy.  After the first
+    // pre_simulate the object's proxy is the youngest, so a box object is body B of every pair.
+    if (is_static(i) && !E.statics[i].compound && j == B_OBJ && (S.obj_first || SHAPE == SHAPE_HULL)) { m.a = (short)j; m.b = (short)i; }
     else { m.a = (short)i; m.b = (short)j; }
-    if (i == B_OBJ) { m.a = (short)j; m.b = (short)i; }      // (tip, obj): tip proxy is older
+    if (i == B_OBJ && SHAPE != SHAPE_HULL) { m.a = (short)j; m.b = (short)i; }      // (tip, box obj): tip proxy is older
     double ta = bs_radius(E, m.a) * E.breaking_factor, tb = bs_radius(E, m.b) * E.breaking_factor;
     m.breaking = ta < tb ? ta : tb;
   }
@@ -451,7 +472,19 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
     Manifold& m = S.man[k];
     Sink sink;
     sink.m = &m; sink.posA = bv[m.a].pos; sink.posB = bv[m.b].pos; sink.RA = bv[m.a].R; sink.RB = bv[m.b].R;
-    box_box(bv[m.a], bv[m.b], sink);
+    if (SHAPE == SHAPE_HULL && (m.a == B_OBJ || m.b == B_OBJ)) {
+      cvx::Scratch scratch;
+      cvx::Shape sh[2];
+      for (int side = 0; side < 2; side++) {
+        int b = side ? m.b : m.a;
+        sh[side].hull = (b == B_OBJ); sh[side].half = bv[b].half; sh[side].verts = E.hull; sh[side].nverts = E.n_hull; sh[side].margin = E.obj_margin;
+      }
+      V3 n, pb; double dist;
+      if (cvx::closest_points(sh[0], bv[m.a].pos, bv[m.a].R, sh[1], bv[m.b].pos, bv[m.b].R, m.breaking, scratch, n, pb, dist))
+        add_contact(sink, n, pb, dist);
+    } else {
+      box_box(bv[m.a], bv[m.b], sink);
+    }
     refresh(m, bv[m.a], bv[m.b]);
   }
 }
@@ -886,19 +919,44 @@ PG_HD void integrate(const EnvDev& E, Sim& S) {
   }
 }
 
+template <int SHAPE>
 PG_HD void substep(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, double* sm, int ss) {
-  collide(E, S, statR);
+  collide<SHAPE>(E, S, statR);
   apply_external(E, S);
   solve(E, S, statR, rs, sm, ss);
   integrate(E, S);
 }
 
-// PyBullet's setCollisionFilterPair re-creates the broadphase proxies of both bodies: every manifold of
-// either body is dropped (plate_env:466, :482)
 PG_HD void drop_manifolds_of(Sim& S, int body) {
   for (int i = 0; i < S.nman;) {
     if (S.man[i].a == body || S.man[i].b == body) { if (i != S.nman - 1) S.man[i] = S.man[S.nman - 1]; S.nman--; }
     else i++;
+  }
+}
+
+// PyBullet's setCollisionFilterPair re-creates the broadphase proxies of both bodies (plate_env:466, :482): every
+// manifold of the body is dropped, and the new proxy is collided against the trees with its TIGHT AABB at once --
+// which decides the order of the pair cache, hence of the contact rows (see collide)
+template <int SHAPE>
+PG_HD void refresh_proxy(const EnvDev& E, Sim& S, int body) {
+  drop_manifolds_of(S, body);
+  DynBody& d = S.dyn[body - MAX_STATICS];
+  d.R = qmat(d.q);
+  BodyView v; v.pos = d.pos; v.R = d.R; v.half = d.half; v.friction = d.friction;
+  V3 lo, hi;
+  tight_aabb<SHAPE>(E, v, body, lo, hi);
+  if (body != B_OBJ) { S.plo[body - B_TIP0] = lo; S.phi[body - B_TIP0] = hi; return; }
+  double depth[2];
+  for (int t = 0; t < 2; t++) {
+    double dd = 1e300;
+    for (int k = 0; k < 3; k++) { double a = S.phi[t][k] - lo[k], b = hi[k] - S.plo[t][k]; double m = a < b ? a : b; if (m < dd) dd = m; }
+    depth[t] = ((S.filter_off >> t) & 1u) ? -1.0 : dd;
+  }
+  S.early = 0;
+  for (int t = 0; t < 2; t++) {
+    // a tip that merely touches the object (overlap < 1e-6) counts only when it is the single active tip (fitted)
+    bool marginal = depth[t] < 1e-6, other_clear = depth[1 - t] >= 1e-6;
+    if (depth[t] >= 0 && !(marginal && other_clear)) S.early |= (1u << t);
   }
 }
 

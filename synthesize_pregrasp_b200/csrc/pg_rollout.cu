@@ -13,6 +13,9 @@
 namespace pg {
 
 #define RK_THREADS PG_BLOCK_THREADS
+// SHAPE: the object's collision shape; box objects never instantiate the GJK / polytope code (and its ~21 KB of
+// per-thread scratch), hull objects (plate) get their own kernel
+template <int SHAPE>
 __global__ void __launch_bounds__(RK_THREADS, 7) rollout_kernel(const EnvDev* __restrict__ env, const double* __restrict__ u,
                                                       const float* __restrict__ noise, int K, int N,
                                                       const int* __restrict__ path, double max_force,
@@ -28,14 +31,18 @@ __global__ void __launch_bounds__(RK_THREADS, 7) rollout_kernel(const EnvDev* __
   out.trace = trace ? trace + (size_t)k * N * SKIP * 7 : nullptr;
   out.iters = iters ? iters + (size_t)k * N * SKIP : nullptr;
   out.settle_iters = nullptr;
-  rollout_one(*env, u, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path, max_force, 1, out, nullptr, 0);   // solver slice: dynamic shared memory, see PG_SM
+  rollout_one<SHAPE>(*env, u, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path, max_force, 1, out, nullptr, 0);   // solver slice: dynamic shared memory, see PG_SM
 }
 
 int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
                    double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st) {
   const int threads = RK_THREADS;
   int blocks = (K + threads - 1) / threads;
-  rollout_kernel<<<blocks, threads, SM_DOUBLES * RK_THREADS * sizeof(double), st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
+  const size_t smem = SM_DOUBLES * RK_THREADS * sizeof(double);
+  if (env->host_env.obj_shape == SHAPE_HULL)
+    rollout_kernel<SHAPE_HULL><<<blocks, threads, smem, st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
+  else
+    rollout_kernel<SHAPE_BOX><<<blocks, threads, smem, st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
   count_launch();
   PG_CUDA(cudaGetLastError());
   return PG_OK;

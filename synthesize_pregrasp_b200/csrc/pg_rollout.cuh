@@ -150,6 +150,7 @@ struct RolloutOut {
 };
 
 // sm / ss: the thread's on-chip solver slice (element i at sm[i*ss]); SM_DOUBLES elements
+template <int SHAPE>
 PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, int N, const int* path,
                         double max_force, int train, RolloutOut out, double* sm, int ss) {
   Sim S;
@@ -175,9 +176,10 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
       t.half = V3(E.tip_half[f][0], E.tip_half[f][1], E.tip_half[f][2]); t.friction = E.tip_friction;
     }
   }
-  S.nman = 0; S.filter_off = 0; S.obj_first = 1; S.last_iterations = 0;
+  S.nman = 0; S.filter_off = 0; S.obj_first = 1; S.last_iterations = 0; S.early = 0;
+  for (int f = 0; f < 2; f++) { S.plo[f] = V3(); S.phi[f] = V3(); }
   S.cons[0].active = 0; S.cons[1].active = 0;
-  substep(E, S, statR, rs, sm, ss);                                                       // :237
+  substep<SHAPE>(E, S, statR, rs, sm, ss);                                                       // :237
   S.obj_first = 0;
   Carry carry;
   for (int f = 0; f < NFING; f++) { carry.on[f] = 0; carry.pos[f] = V3(); carry.norm[f] = V3(); }
@@ -197,17 +199,17 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
         V3 g = o.pos + mul(R, cur_pos[i]);
         if (!check_clearance(E, g)) g = V3(100.0, 100.0, 100.0);
         S.filter_off |= (1u << i);
-        drop_manifolds_of(S, B_TIP0 + i);
-        drop_manifolds_of(S, B_OBJ);
+        refresh_proxy<SHAPE>(E, S, B_TIP0 + i);
+        refresh_proxy<SHAPE>(E, S, B_OBJ);
         DynBody& t = S.dyn[1 + i];
         t.pos = g; t.q = qnormalize(o.q); t.v = V3(); t.w = V3(); t.R = qmat(t.q);
         S.cons[i].pivotB = g; S.cons[i].frameB = R; S.cons[i].max_impulse = E.default_max_impulse; S.cons[i].active = 1;
       }
-      substep(E, S, statR, rs, sm, ss);
+      substep<SHAPE>(E, S, statR, rs, sm, ss);
       for (int i = 0; i < NFING; i++) {
         S.filter_off &= ~(1u << i);
-        drop_manifolds_of(S, B_TIP0 + i);
-        drop_manifolds_of(S, B_OBJ);
+        refresh_proxy<SHAPE>(E, S, B_TIP0 + i);
+        refresh_proxy<SHAPE>(E, S, B_OBJ);
       }
     }
     // ---- servo loop :504-533
@@ -225,14 +227,14 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
         V3 tar = (o.pos + mul(R, cur_pos[i])) + v_g;
         S.cons[i].pivotB = tar; S.cons[i].frameB = R; S.cons[i].max_impulse = max_force * E.dt;
       }
-      substep(E, S, statR, rs, sm, ss);
+      substep<SHAPE>(E, S, statR, rs, sm, ss);
       if (out.iters) out.iters[j * SKIP + t] = S.last_iterations;
     }
     // ---- settle + metric :556-603 (train mode)
     if (j == N - 1 && train) {
       double m0 = (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
       for (int s = 0; s < E.settle_substeps; s++) {
-        substep(E, S, statR, rs, sm, ss);
+        substep<SHAPE>(E, S, statR, rs, sm, ss);
         if (out.settle_iters) out.settle_iters[s] = S.last_iterations;
       }
       if (out.metric) *out.metric = m0 + (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
