@@ -20,7 +20,7 @@ extern "C" {
 #define PG_OK 0
 #define PG_ERR_INVALID 1      /* bad argument */
 #define PG_ERR_CUDA 2         /* CUDA runtime error (text in pg_last_error) */
-#define PG_ERR_UNSUPPORTED 3  /* valid reference feature not built yet (hull / cylinder objects) */
+#define PG_ERR_UNSUPPORTED 3  /* valid reference feature not built */
 
 #define PG_ACTION_DIM 48      /* 2 fingers x (7 knots x 3 + 2 position params + on/off), plate_env:145-147 */
 #define PG_CONTROL_SKIP 50    /* plate_env:51 */
@@ -45,7 +45,8 @@ typedef struct PgScoreWeights { /* neurals/network.py:434-441 LargeScoreFunction
 
 typedef struct PgEnvSpec {     /* the constructor kwargs + literals of envs/<env>_contact_graph_env.py */
   /* dynamic object */
-  int32_t obj_shape;           /* 0 box, 1 convex hull, 2 z-cylinder */
+  int32_t obj_shape;           /* 0 box, 1 convex hull of a URDF mesh (child of a compound shape), 2 URDF <cylinder>:
+                                  the 64-vertex prism hull PyBullet builds for it (hull = its vertices) */
   int32_t n_hull;
   double obj_half[3];
   const double* hull;          /* [n_hull,3] or NULL */

@@ -123,7 +123,9 @@ class EnvSim:
         names = s["static_names"]
         for name in s["order"]:
             if name == "obj":
-                self.obj = self._add(s["obj_shape"], s["obj_half"], s.get("obj_hull"), s["obj_mass"], s["obj_pos"],
+                # shape 1: URDF mesh = hull inside a btCompoundShape; shape 2: URDF <cylinder> = bare 64-vertex prism hull
+                shape = 1 if (s["obj_shape"] == 2 and s.get("obj_hull") is not None) else s["obj_shape"]
+                self.obj = self._add(shape, s["obj_half"], s.get("obj_hull"), s["obj_mass"], s["obj_pos"],
                                      s["obj_quat"], s["obj_friction"],
                                      compound=bool(self.params.get("obj_compound", s["obj_shape"] == 1)))
             else:

@@ -109,6 +109,7 @@ struct Shape {
   int type = SH_BOX;
   V3 half;                 // box: full half extents (margin included, as btBoxShape keeps them)
   std::vector<V3> verts;   // hull vertices (core shape; margin is added on top)
+  bool in_compound = false; // hull child of a btCompoundShape (URDF mesh)
   double margin = 0.001;   // [H] gUrdfDefaultCollisionMargin / m_defaultCollisionMargin
   double radius = 0, halfh = 0;  // cylinder Z
 };
@@ -172,6 +173,7 @@ struct Params {
   double aabb_margin = 0.02;      // contact threshold added to AABBs
   double max_coord_vel = 100.0;   // btMultiBody::m_maxCoordinateVelocity
   int pair_order_mode = -1;       // -1: by object type; 0: box-object order; 1: compound-object order (see collide)
+  int manifold_reverse = 0;       // debugging: reverse the final manifold order
   int manifold_order3 = 0;        // debugging: explicit order (digits, creation indices) when exactly 3 manifolds are solved
   int manifold_order = 0;         // 0: emulate quickSort of dispatcher order; k>=1: (k-1)-th permutation of creation order
   int constraint_reverse = 1;     // [H] quickSort of equal island ids reverses the two servo constraints
@@ -209,22 +211,28 @@ struct World {
 
 static void update_cache(Body& b) { b.R = qmat(b.q); }
 
-static double bounding_radius(const Shape& s) {
-  // btCollisionShape::getBoundingSphere via the local AABB (margin included), centre + radius
-  if (s.type == SH_BOX) return len(s.half);
-  if (s.type == SH_CYL) return len(V3(s.radius, s.radius, s.halfh));  // btCylinderShape aabb = half extents
+// Hull AABBs (btPolyhedralConvexAabbCachingShape): the cached local AABB is the vertex extent + margin, getAabb() adds
+// the margin once more (child / tight AABB = extent + 2 margins); a btCompoundShape wrapper (URDF mesh) adds its own
+// margin on top for the broadphase AABB, the bounding sphere and, through them, the contact breaking threshold.
+static double g_hull_aabb_margins = 2.0, g_compound_margin = 0.001;
+static void hull_extent(const Shape& s, double margins, bool with_compound, V3& c, V3& e) {
   V3 lo(1e300, 1e300, 1e300), hi(-1e300, -1e300, -1e300);
   for (auto& v : s.verts) for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], v[k]); hi[k] = std::max(hi[k], v[k]); }
-  lo = lo - V3(s.margin, s.margin, s.margin); hi = hi + V3(s.margin, s.margin, s.margin);
-  return len((hi - lo) * 0.5) + len((hi + lo) * 0.5);
+  double m = margins * s.margin + ((with_compound && s.in_compound) ? g_compound_margin : 0.0);
+  c = (hi + lo) * 0.5; e = (hi - lo) * 0.5 + V3(m, m, m);
+}
+static double bounding_radius(const Shape& s) {
+  // btCollisionShape::getBoundingSphere via getAabb(identity): half diagonal, plus the centre offset (getAngularMotionDisc)
+  if (s.type == SH_BOX) return len(s.half);
+  if (s.type == SH_CYL) return len(V3(s.radius, s.radius, s.halfh));  // btCylinderShape aabb = half extents
+  V3 c, e; hull_extent(s, g_hull_aabb_margins, true, c, e);
+  return len(e) + len(c);
 }
 
 static void local_aabb(const Shape& s, V3& c, V3& e) {
   if (s.type == SH_BOX) { c = V3(); e = s.half; return; }
   if (s.type == SH_CYL) { c = V3(); e = V3(s.radius, s.radius, s.halfh); return; }
-  V3 lo(1e300, 1e300, 1e300), hi(-1e300, -1e300, -1e300);
-  for (auto& v : s.verts) for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], v[k]); hi[k] = std::max(hi[k], v[k]); }
-  c = (hi + lo) * 0.5; e = (hi - lo) * 0.5 + V3(s.margin, s.margin, s.margin);
+  hull_extent(s, g_hull_aabb_margins, true, c, e);
 }
 
 static void compute_aabb(Body& b, double extra) {
@@ -247,7 +255,8 @@ static V3 shape_inertia(const Shape& s, double mass) {
   } else {
     // btCompoundShape::calculateLocalInertia: box inertia of the compound's AABB.  The cached hull AABB carries the
     // margin three times (support with margin + recalcLocalAabb + btTransformAabb) and the compound adds its own
-    V3 c, e; local_aabb(s, c, e);
+    // (btPolyhedralConvexShape::calculateLocalInertia for a bare hull gives the same: getAabb(identity) + one margin)
+    V3 c, e; hull_extent(s, 1.0, false, c, e);
     e = e + V3(g_hull_inertia_pad, g_hull_inertia_pad, g_hull_inertia_pad);
     lx = 2 * e.x; ly = 2 * e.y; lz = 2 * e.z;
   }
@@ -605,9 +614,10 @@ static bool aabb_overlap(const Body& a, const Body& b) {
 static bool pair_overlap(const World& w, const Body& a, const Body& b) {
   if (!aabb_overlap(a, b)) return false;
   if (a.compound || b.compound) {
-    double e = w.P.aabb_margin;
+    double ea = w.P.aabb_margin + (a.shape.in_compound ? g_compound_margin : 0.0);
+    double eb = w.P.aabb_margin + (b.shape.in_compound ? g_compound_margin : 0.0);
     for (int k = 0; k < 3; k++)
-      if (a.aabb_lo[k] + e > b.aabb_hi[k] - e || a.aabb_hi[k] - e < b.aabb_lo[k] + e) return false;
+      if (a.aabb_lo[k] + ea > b.aabb_hi[k] - eb || a.aabb_hi[k] - ea < b.aabb_lo[k] + eb) return false;
   }
   return true;
 }
@@ -738,6 +748,7 @@ static void collide(World& w) {
     else if (bj.compound) { m.a = j; m.b = i; }
     else if ((bi.uid < bj.uid) != (w.P.pair_flip != 0)) { m.a = i; m.b = j; }
     else { m.a = j; m.b = i; }
+    if (w.P.debug == 1) fprintf(stderr, "oracle new manifold %d-%d  lo_i %.5f %.5f %.5f hi_i %.5f %.5f %.5f | lo_j %.5f %.5f %.5f hi_j %.5f %.5f %.5f\n", i, j, bi.aabb_lo.x, bi.aabb_lo.y, bi.aabb_lo.z, bi.aabb_hi.x, bi.aabb_hi.y, bi.aabb_hi.z, bj.aabb_lo.x, bj.aabb_lo.y, bj.aabb_lo.z, bj.aabb_hi.x, bj.aabb_hi.y, bj.aabb_hi.z);
     double ta = bounding_radius(w.bodies[m.a].shape) * w.P.breaking_factor;
     double tb = bounding_radius(w.bodies[m.b].shape) * w.P.breaking_factor;
     m.breaking = std::min(ta, tb);
@@ -983,6 +994,7 @@ static void solve(World& w) {
       for (int k = 0; k < P.manifold_order - 1; k++) std::next_permutation(mlist.begin(), mlist.end());
     }
     if (P.debug == 1) { fprintf(stderr, "step %d solve order:", w.step_count); for (int mi : mlist) fprintf(stderr, " [%d](%d-%d n%d)", mi, w.manifolds[mi].a, w.manifolds[mi].b, w.manifolds[mi].n); fprintf(stderr, "\n"); }
+    if (P.manifold_reverse) std::reverse(mlist.begin(), mlist.end());
     std::vector<SolverRow> nc, normal, fric;
     w.dv.assign(6 * nb, 0.0);
     w.ws.assign(6 * nb, 0.0);
@@ -1123,8 +1135,10 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(default_max_impulse) S(debug)
 #undef S
+  if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
+  if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }
   if (!strcmp(name, "hull_inertia_pad")) { g_hull_inertia_pad = v; return; }
   if (!strcmp(name, "pen_tie")) { g_pen_tie = v; return; }
   if (!strcmp(name, "epa_variant")) { epa2::g_epa_variant = (int)v; return; }
@@ -1147,6 +1161,7 @@ int pgo_add_body(void* h, int type, const double* half, const double* verts, int
   b.q = qnormalize(Q4{quat[0], quat[1], quat[2], quat[3]});
   b.friction = friction;
   b.compound = compound != 0;
+  b.shape.in_compound = b.compound && type == SH_HULL;
   b.uid = w.next_uid++;
   update_cache(b);
   w.bodies.push_back(b);

@@ -7,13 +7,19 @@
 namespace pgo {
 
 static long g_epa_events = 0, g_gjk_calls = 0;
-static double g_pen_tie = 1e-13;   // [H] when the early-exit GJK distance and the EPA depth agree to rounding (vertex-face contact,
-                                   // 1-2 mm deep) the recorded plate trajectory shows Bullet keeping the EPA result every time
+static double g_pen_tie = 0.0;   // debugging: bias of the EPA-vs-GJK depth comparison (Bullet: none)
 
 static V3 support_core_local(const Shape& sh, V3 d) {
   if (sh.type == SH_BOX) {
     V3 h = sh.half - V3(sh.margin, sh.margin, sh.margin);          // getImplicitShapeDimensions
     return V3(d.x >= 0 ? h.x : -h.x, d.y >= 0 ? h.y : -h.y, d.z >= 0 ? h.z : -h.z);   // btFsels
+  }
+  if (sh.type == SH_CYL) {
+    // btConvexShape::localGetSupportVertexWithoutMarginNonVirtual, cylinder with up axis Z (URDF <cylinder>)
+    double radius = sh.radius - sh.margin, hh = sh.halfh - sh.margin;
+    double s = std::sqrt(d.x * d.x + d.y * d.y);
+    if (s != 0.0) { double k = radius / s; return V3(d.x * k, d.y * k, d.z < 0.0 ? -hh : hh); }
+    return V3(radius, 0.0, d.z < 0.0 ? -hh : hh);
   }
   double best = -1e300; int bi = 0;                                  // btVector3::maxDot: first strict maximum
   for (size_t i = 0; i < sh.verts.size(); i++) { double t = dot(sh.verts[i], d); if (t > best) { best = t; bi = (int)i; } }
@@ -197,7 +203,7 @@ static void convex_convex(World& w, Body& A, Body& B, ContactSink& out) {
     if (lsq > kEps * kEps) {
       double rlen = 1.0 / std::sqrt(lsq);
       normalInB = normalInB * rlen;
-      double s = std::sqrt(sqd);
+      double s = std::sqrt(lsq);
       pointOnA = pointOnA - axis * (marginA / s);
       pointOnB = pointOnB + axis * (marginB / s);
       distance = (1.0 / rlen) - margin;

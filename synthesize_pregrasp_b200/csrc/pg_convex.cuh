@@ -633,7 +633,7 @@ PG_HDN bool closest_points(const Shape& sA, V3 posA, const M3& RA, const Shape& 
     if (lsq > EPS * EPS) {
       double rlen = 1.0 / sqrt(lsq);
       normalInB = normalInB * rlen;
-      double s = sqrt(sqd);                      // stale after the early exit above, as in Bullet
+      double s = sqrt(lsq);
       pointOnA = pointOnA - axis * (mA / s);
       pointOnB = pointOnB + axis * (mB / s);
       distance = (1.0 / rlen) - margin;
@@ -652,8 +652,7 @@ PG_HDN bool closest_points(const Shape& sA, V3 posA, const M3& RA, const Shape& 
         if (lsq > EPS * EPS) {
           tn = vdiv(tn, sqrt(lsq));
           double d2 = -len(tA - tB);
-          // near-ties (vertex-face contact 1-2 mm deep) go to the polytope result: fitted to the recorded plate trajectory
-          if (!is_valid || d2 < distance + 1e-13) { distance = d2; pointOnA = tA; pointOnB = tB; normalInB = tn; is_valid = true; }
+          if (!is_valid || d2 < distance) { distance = d2; pointOnA = tA; pointOnB = tB; normalInB = tn; is_valid = true; }
         }
       } else {
         double d2 = len(tA - tB) - margin;

@@ -22,10 +22,11 @@ struct EnvDev {
       aabb_margin, max_coord_vel, default_max_impulse;
   int iterations, pad0;
   // object
-  int obj_shape, n_hull;
+  int obj_shape, n_hull, obj_compound;
   double obj_half[3], obj_mass, obj_inertia[3], obj_pos[3], obj_quat[4], obj_friction, obj_margin, obj_radius_bs;
   double hull[MAX_HULL * 3];
-  double obj_aabb_c[3], obj_aabb_e[3];   // local AABB centre / half extent (margin included) of the object shape
+  double obj_aabb_c[3], obj_aabb_e[3];   // local AABB centre / half extent of the object's broadphase AABB (hull: extent + 2 margins + compound margin)
+  double obj_compound_margin;            // what the compound wrapper adds on top of the child (tight) AABB
   // static scene
   int n_static, floor_index;
   BoxBody statics[MAX_STATICS];

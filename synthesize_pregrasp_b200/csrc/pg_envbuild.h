@@ -12,8 +12,8 @@ namespace pg {
 static inline double box_radius(const double* h) { return sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]); }
 
 static inline int build_envdev(const PgEnvSpec* sp, EnvDev& E, std::string& err) {
-  if (sp->obj_shape != SHAPE_BOX && sp->obj_shape != SHAPE_HULL) { err = "cylinder objects (waterbottle) are not built in this round"; return PG_ERR_UNSUPPORTED; }
-  if (sp->obj_shape == SHAPE_HULL && (sp->n_hull < 4 || sp->n_hull > MAX_HULL || !sp->hull)) { err = "hull needs 4..64 vertices"; return PG_ERR_INVALID; }
+  if (sp->obj_shape != SHAPE_BOX && sp->obj_shape != SHAPE_HULL && sp->obj_shape != SHAPE_CYL) { err = "unknown object shape"; return PG_ERR_INVALID; }
+  if (sp->obj_shape != SHAPE_BOX && (sp->n_hull < 4 || sp->n_hull > MAX_HULL || !sp->hull)) { err = "hull needs 4..64 vertices"; return PG_ERR_INVALID; }
   if (sp->n_static < 1 || sp->n_static > MAX_STATICS || sp->n_regions > MAX_REGIONS || sp->n_states > MAX_STATES || !sp->csg) {
     err = "spec out of supported bounds"; return PG_ERR_INVALID;
   }
@@ -23,6 +23,7 @@ static inline int build_envdev(const PgEnvSpec* sp, EnvDev& E, std::string& err)
   E.lin_damping = 0.04; E.ang_damping = 0.04; E.breaking_factor = 0.02; E.aabb_margin = 0.02; E.max_coord_vel = 100.0;
   E.default_max_impulse = 500.0; E.iterations = 50;
   E.obj_shape = sp->obj_shape; E.n_hull = 0;
+  E.obj_compound = (sp->obj_shape == SHAPE_HULL);      // URDF mesh: hull wrapped in a btCompoundShape; URDF cylinder: bare hull
   for (int i = 0; i < 3; i++) { E.obj_half[i] = sp->obj_half[i]; E.obj_pos[i] = sp->obj_pos[i]; }
   for (int i = 0; i < 4; i++) E.obj_quat[i] = sp->obj_quat[i];
   E.obj_mass = sp->obj_mass; E.obj_friction = sp->obj_friction; E.obj_margin = 0.001;
@@ -32,9 +33,7 @@ static inline int build_envdev(const PgEnvSpec* sp, EnvDev& E, std::string& err)
     E.obj_radius_bs = box_radius(E.obj_half);
     for (int i = 0; i < 3; i++) { E.obj_aabb_c[i] = 0; E.obj_aabb_e[i] = E.obj_half[i]; }
   } else {
-    // URDF mesh -> btCompoundShape(btConvexHullShape): inertia = box inertia of the compound's AABB, which carries the
-    // margin three times (recorded plate trajectory: pad 0.003 over the vertex extents); bounding sphere from the
-    // margin-inclusive AABB
+    // URDF mesh -> btCompoundShape(btConvexHullShape); URDF <cylinder> -> bare 64-vertex btConvexHullShape
     E.n_hull = sp->n_hull;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int v = 0; v < sp->n_hull; v++) for (int i = 0; i < 3; i++) {
@@ -42,10 +41,15 @@ static inline int build_envdev(const PgEnvSpec* sp, EnvDev& E, std::string& err)
       if (x < lo[i]) lo[i] = x;
       if (x > hi[i]) hi[i] = x;
     }
+    // btPolyhedralConvexAabbCachingShape: cached local AABB = vertex extent + margin, getAabb() adds the margin again
+    // (child / tight AABB: extent + 2 margins); the btCompoundShape of a URDF mesh adds its own margin for the
+    // broadphase AABB and the bounding sphere; calculateLocalInertia uses the box of extent + 3 margins either way
     double l[3], r2 = 0, c2 = 0;
+    E.obj_compound_margin = E.obj_compound ? 0.001 : 0.0;
     for (int i = 0; i < 3; i++) {
-      E.obj_aabb_c[i] = 0.5 * (hi[i] + lo[i]); E.obj_aabb_e[i] = 0.5 * (hi[i] - lo[i]) + E.obj_margin;
-      l[i] = 2 * (E.obj_aabb_e[i] + 0.002);
+      double he = 0.5 * (hi[i] - lo[i]);
+      E.obj_aabb_c[i] = 0.5 * (hi[i] + lo[i]); E.obj_aabb_e[i] = he + 2 * E.obj_margin + E.obj_compound_margin;
+      l[i] = 2 * ((he + E.obj_margin) + 0.002);
       r2 += E.obj_aabb_e[i] * E.obj_aabb_e[i]; c2 += E.obj_aabb_c[i] * E.obj_aabb_c[i];
     }
     double m = E.obj_mass;

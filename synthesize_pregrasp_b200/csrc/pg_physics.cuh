@@ -422,12 +422,14 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
     tight_aabb<SHAPE>(E, bv[b], b, lo[b], hi[b]);
     lo[b] = lo[b] - V3(am, am, am); hi[b] = hi[b] + V3(am, am, am);
   }
-  auto is_compound = [&](int b) -> bool { return is_static(b) ? (E.statics[b].compound != 0) : (SHAPE == SHAPE_HULL && b == B_OBJ); };
+  auto is_compound = [&](int b) -> bool { return is_static(b) ? (E.statics[b].compound != 0) : (SHAPE == SHAPE_HULL && b == B_OBJ && E.obj_compound); };
   auto pair_overlap = [&](int a, int b) -> bool {
     if (!overlap(lo[a], hi[a], lo[b], hi[b])) return false;
     if (is_compound(a) || is_compound(b)) {   // btCompound(Compound)CollisionAlgorithm: child manifold lives only while the TIGHT aabbs overlap
+      double ea = am + ((SHAPE == SHAPE_HULL && a == B_OBJ) ? E.obj_compound_margin : 0.0);
+      double eb = am + ((SHAPE == SHAPE_HULL && b == B_OBJ) ? E.obj_compound_margin : 0.0);
       for (int k = 0; k < 3; k++)
-        if (lo[a][k] + am > hi[b][k] - am || hi[a][k] - am < lo[b][k] + am) return false;
+        if (lo[a][k] + ea > hi[b][k] - eb || hi[a][k] - ea < lo[b][k] + eb) return false;
     }
     return true;
   };
@@ -458,13 +460,16 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
     bool have = false;
     for (int k = 0; k < S.nman; k++) if ((S.man[k].a == i && S.man[k].b == j) || (S.man[k].a == j && S.man[k].b == i)) have = true;
     if (have || S.nman >= MAXM) continue;
+#if defined(PG_HOST_DEBUG) && !defined(__CUDA_ARCH__)
+    fprintf(stderr, "host new manifold %d-%d  lo_i %.5f %.5f %.5f hi_i %.5f %.5f %.5f | lo_j %.5f %.5f %.5f hi_j %.5f %.5f %.5f\n", i, j, lo[i].x, lo[i].y, lo[i].z, hi[i].x, hi[i].y, hi[i].z, lo[j].x, lo[j].y, lo[j].z, hi[j].x, hi[j].y, hi[j].z);
+#endif
     Manifold& m = S.man[S.nman++];
     m.n = 0;
     // body A: a compound shape always (floor; hull object), otherwise the older broadphase proxy.  After the first
     // pre_simulate the object's proxy is the youngest, so a box object is body B of every pair.
-    if (is_static(i) && !E.statics[i].compound && j == B_OBJ && (S.obj_first || SHAPE == SHAPE_HULL)) { m.a = (short)j; m.b = (short)i; }
+    if (is_static(i) && !E.statics[i].compound && j == B_OBJ && (S.obj_first || is_compound(B_OBJ))) { m.a = (short)j; m.b = (short)i; }
     else { m.a = (short)i; m.b = (short)j; }
-    if (i == B_OBJ && SHAPE != SHAPE_HULL) { m.a = (short)j; m.b = (short)i; }      // (tip, box obj): tip proxy is older
+    if (i == B_OBJ && !is_compound(B_OBJ)) { m.a = (short)j; m.b = (short)i; }      // (tip, obj): tip proxy is older
     double ta = bs_radius(E, m.a) * E.breaking_factor, tb = bs_radius(E, m.b) * E.breaking_factor;
     m.breaking = ta < tb ? ta : tb;
   }
@@ -714,6 +719,9 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
     mval[k] = k;
   }
   bt_quicksort(mkey, mval, S.nman);
+#if defined(PG_HOST_DEBUG) && !defined(__CUDA_ARCH__)
+  { static int step = 0; step++; fprintf(stderr, "host step %d order:", step); for (int k = 0; k < S.nman; k++) fprintf(stderr, " [%d](%d-%d n%d)", mval[k], S.man[mval[k]].a, S.man[mval[k]].b, S.man[mval[k]].n); fprintf(stderr, "\n"); }
+#endif
   int ckey[2], cval[2], ncons = 0;
   for (int c = 0; c < 2; c++) if (S.cons[c].active) { ckey[ncons] = tag[1 + c]; cval[ncons] = c; ncons++; }
   bt_quicksort(ckey, cval, ncons);

@@ -39,7 +39,7 @@ int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N
   const int threads = RK_THREADS;
   int blocks = (K + threads - 1) / threads;
   const size_t smem = SM_DOUBLES * RK_THREADS * sizeof(double);
-  if (env->host_env.obj_shape == SHAPE_HULL)
+  if (env->host_env.obj_shape != SHAPE_BOX)
     rollout_kernel<SHAPE_HULL><<<blocks, threads, smem, st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
   else
     rollout_kernel<SHAPE_BOX><<<blocks, threads, smem, st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);

@@ -56,7 +56,7 @@ class EnvSpec:
     # --- dynamic object -------------------------------------------------------------
     obj_shape: int
     obj_half: Tuple[float, float, float]          # box half extents | (r, r, half_len) for the cylinder
-    obj_hull: Optional[np.ndarray]                # [V,3] for SHAPE_HULL
+    obj_hull: Optional[np.ndarray]                # [V,3] for SHAPE_HULL (mesh, inside a compound) and SHAPE_CYLINDER (bare prism hull)
     obj_mass: float
     obj_pos: Tuple[float, float, float]
     obj_quat: Tuple[float, float, float, float]
@@ -176,6 +176,23 @@ def bullet_hull_vertices(obj_vertices: np.ndarray) -> np.ndarray:
     over the settling phase only with these snapped vertices (3.3e-8 with the raw OBJ numbers).
     """
     v = np.asarray(obj_vertices, np.float64).astype(np.float32).astype(np.float64)
+    lo, hi = v.min(0), v.max(0)
+    s = (hi - lo) / 10216.0
+    c = (lo + hi) * 0.5
+    return np.trunc((v - c) * (1.0 / s)) * s + c
+
+
+def bullet_cylinder_hull(radius: float, half_len: float) -> np.ndarray:
+    """What PyBullet collides with for a URDF <cylinder> (waterbottle.urdf): without URDF_USE_IMPLICIT_CYLINDER the
+    importer builds a 32-sided prism as a btConvexHullShape -- 64 vertices (r sin a_i, r cos a_i, +-h), a_i = 2 pi i/32
+    with i/32 evaluated in float -- and snaps it through optimizeConvexHull like any other hull.  The recorded
+    waterbottle trajectory confirms the hull (box-of-AABB inertia), not the analytic cylinder."""
+    v = []
+    for i in range(32):
+        a = 6.283185307179586232 * float(np.float32(i) / np.float32(32))
+        v.append([radius * np.sin(a), radius * np.cos(a), half_len])
+        v.append([radius * np.sin(a), radius * np.cos(a), -half_len])
+    v = np.asarray(v, np.float64)
     lo, hi = v.min(0), v.max(0)
     s = (hi - lo) / 10216.0
     c = (lo + hi) * 0.5
@@ -310,7 +327,8 @@ def make_spec(env: str) -> EnvSpec:
         tris = np.concatenate([_o3d_cylinder_tris(0.045, 0.22, (0, -0.1, 0.11)),
                                _o3d_cylinder_tris(0.045, 0.22, (0, 0.1, 0.11))])
         return EnvSpec(
-            name=env, obj_shape=SHAPE_CYLINDER, obj_half=(0.041, 0.041, 0.11), obj_hull=None,  # assets/waterbottle.urdf
+            name=env, obj_shape=SHAPE_CYLINDER, obj_half=(0.041, 0.041, 0.11),
+            obj_hull=bullet_cylinder_hull(0.041, 0.11),                                       # assets/waterbottle.urdf
             obj_mass=1.0, obj_pos=(0.0, 0.0, 0.115), obj_quat=_ID, obj_friction=70.0,        # setup_pybullet.py:87
             statics=[StaticBox(pos=(0.0, 0.0, -5.0), quat=_ID, friction=70.0, name="floor", **_FLOOR_BIG)] + walls,
             order=("floor", "obj", "w1", "w2", "w3"),

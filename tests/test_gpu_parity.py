@@ -30,7 +30,7 @@ def _oracle_trace(spec, u, noise_row, F, train=False):
     return rs
 
 
-@pytest.mark.parametrize("exp", ["plate_20.0", "foodbox_20.0", "keyboard_20.0", "keyboard_scale_20.0", "wall_laptop_20.0", "cardboard_20.0"])
+@pytest.mark.parametrize("exp", ["plate_20.0", "waterbottle_20.0", "foodbox_20.0", "keyboard_20.0", "keyboard_scale_20.0", "wall_laptop_20.0", "cardboard_20.0"])
 def test_physics_kernel_on_recorded_controls(EN, exp):
     """K=1 replay of the reference's recorded u: kernel vs oracle (tight) and vs the PyBullet recording."""
     from synthesize_pregrasp_b200.envspec import make_spec
@@ -47,7 +47,7 @@ def test_physics_kernel_on_recorded_controls(EN, exp):
     assert e[0] <= 1e-6 and e[1] <= 1e-6, e[:2]            # first substeps reproduce PyBullet's recording
 
 
-@pytest.mark.parametrize("env,F", [("plate", 20.0), ("foodbox", 20.0), ("bookshelf", 50.0), ("keyboard", 20.0)])
+@pytest.mark.parametrize("env,F", [("plate", 20.0), ("waterbottle", 20.0), ("foodbox", 20.0), ("bookshelf", 50.0), ("keyboard", 20.0)])
 def test_physics_kernel_random_batch(EN, env, F):
     """Seeded noise batch, tolerance 1e-4 on the object pose at the cost-evaluation instants (north_star)."""
     from synthesize_pregrasp_b200.envspec import make_spec
@@ -76,7 +76,7 @@ def test_physics_kernel_random_batch(EN, env, F):
     assert ok >= int(0.75 * K), ok
 
 
-@pytest.mark.parametrize("env", ["plate", "foodbox", "bookshelf", "keyboard", "laptop", "cardboard"])
+@pytest.mark.parametrize("env", ["plate", "waterbottle", "foodbox", "bookshelf", "keyboard", "laptop", "cardboard"])
 def test_cost_kernel_matches_oracle(EN, env):
     from oracle import cost as CO
     from oracle import scorenet as SN

@@ -100,6 +100,8 @@ PHYS = {  # exp: (rows to check, tolerance on pose) -- achieved tolerances, see 
     "foodbox_20.0": (range(0, 11), 1e-7), "keyboard_20.0": (range(0, 31), 1e-7), "keyboard_scale_20.0": (range(0, 50), 2e-7),
     "wall_laptop_20.0": (range(0, 6), 1e-9), "cardboard_20.0": (range(0, 50), 2e-6),
     "plate_20.0": (range(0, 37), 1e-8),      # hull object: GJK + EPA narrowphase, compound pair rules
+    "waterbottle_20.0": (range(0, 3), 1e-9),  # URDF cylinder = 64-vertex prism hull; later rows: manifold order of the
+                                              # late floor contact is not recovered
 }
 
 
@@ -162,7 +164,7 @@ def test_product_kernel_logic_on_host_matches_oracle():
                            "-o", so, os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")])
     H = C.CDLL(so)
     rng = np.random.RandomState(7)
-    for env, F in (("keyboard", 20.0), ("bookshelf", 50.0), ("laptop", 20.0), ("plate", 20.0)):
+    for env, F in (("keyboard", 20.0), ("bookshelf", 50.0), ("laptop", 20.0), ("plate", 20.0), ("waterbottle", 20.0)):
         spec = make_spec(env)
         cs, keep = _abi.make_c_spec(spec)
         u = 0.8 * rng.randn(2, 48)
