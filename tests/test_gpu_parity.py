@@ -232,8 +232,9 @@ def test_optimizer_api_runs_and_improves(EN):
 
 def test_errors_are_reported_not_swallowed(EN):
     from synthesize_pregrasp_b200.envspec import make_spec
+    import dataclasses
     with pytest.raises(RuntimeError):
-        EN.RolloutEngine(make_spec("waterbottle"), device=0)    # cylinder objects: PG_ERR_UNSUPPORTED this round
+        EN.RolloutEngine(dataclasses.replace(make_spec("plate"), obj_hull=None), device=0)    # hull object without vertices
     eng = EN.RolloutEngine(make_spec("foodbox"), device=0)
     with pytest.raises(RuntimeError):
         eng.rollout(np.zeros((2, 48)), None, [0, 7], 20.0, K=1)   # contact state out of range
