@@ -158,7 +158,7 @@ def lib():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(os.environ.get("PREGRASP_B200_LIB", LIB_PATH))     # override: kernel-variant experiments only
     vp, i32, f64 = C.c_void_p, C.c_int, C.c_double
     L.pg_last_error.restype = C.c_char_p
     L.pg_version.restype = C.c_char_p

@@ -765,6 +765,9 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
   }
   for (int c = 0; c < ncons; c++) setup_fixed_rows(E, S, sm, ss, cval[c], rs.nc);
   S.last_iterations = 0;
+#if defined(PG_HOST_STATS) && !defined(__CUDA_ARCH__)
+  { extern long g_stat_pts[32], g_stat_nc[16]; g_stat_pts[rs.n_pts < 31 ? rs.n_pts : 31]++; g_stat_nc[rs.nc.n < 15 ? rs.nc.n : 15]++; }
+#endif
   if (rs.nc.n == 0 && rs.n_pts == 0) return;
   double max_imp[2] = {0, 0};
   for (int c = 0; c < ncons; c++) max_imp[c] = S.cons[cval[c]].max_impulse;

@@ -4,6 +4,10 @@
 #include "../../synthesize_pregrasp_b200/csrc/pg_envbuild.h"
 #include "../../synthesize_pregrasp_b200/csrc/pg_rollout.cuh"
 
+#ifdef PG_HOST_STATS
+namespace pg { long g_stat_pts[32], g_stat_nc[16]; }
+extern "C" void hostsim_stats(long* pts, long* nc) { for (int i = 0; i < 32; i++) pts[i] = pg::g_stat_pts[i]; for (int i = 0; i < 16; i++) nc[i] = pg::g_stat_nc[i]; }
+#endif
 static int* g_settle = nullptr;
 extern "C" void hostsim_set_settle_buffer(int* p) { g_settle = p; }
 extern "C" int hostsim_rollout(const PgEnvSpec* sp, const double* u, const float* noise, int K, int N, const int* path,

@@ -1,0 +1,9 @@
+#!/bin/bash
+# times the default workload with each kernel-variant library found in synthesize_pregrasp_b200/_variants/
+mkdir -p gpurun_out
+for so in synthesize_pregrasp_b200/libpregrasp_b200.so synthesize_pregrasp_b200/_variants/*.so; do
+  for wl in ${WORKLOADS:-bookshelf_K65536}; do
+    PREGRASP_B200_LIB=$PWD/$so timeout 600 python bench.py --steps 2 --warmup 1 --cpu-sample 1 --workload $wl > gpurun_out/variant.log 2>&1
+    echo "$so $wl $(tail -1 gpurun_out/variant.log | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(d["ms_per_step"], d["stage_ms"])' 2>&1 | tail -1)" | tee -a gpurun_out/variants_summary.txt
+  done
+done
