@@ -23,7 +23,7 @@ struct Xf { V3 o; M3 R; };
 PG_HD double len2(V3 a) { return dot(a, a); }
 PG_HD V3 vdiv(V3 a, double s) { return a * (1.0 / s); }
 
-PG_HD V3 support_core(const Shape& s, V3 d) {
+PG_HDN V3 support_core(const Shape& s, V3 d) {
   if (!s.hull) {
     V3 h(s.half.x - s.margin, s.half.y - s.margin, s.half.z - s.margin);
     return V3(d.x >= 0 ? h.x : -h.x, d.y >= 0 ? h.y : -h.y, d.z >= 0 ? h.z : -h.z);
@@ -160,7 +160,7 @@ struct Mink {
   M3 to1, to0; V3 to0_o;
   bool margins;
 };
-PG_HD V3 mink_ls(const Mink& md, const Shape& s, V3 d) {
+PG_HDN V3 mink_ls(const Mink& md, const Shape& s, V3 d) {
   if (!md.margins) return support_core(s, d);
   V3 n = d;
   if (len2(n) < 2.220446049250313e-16 * 2.220446049250313e-16) n = V3(-1, -1, -1);
@@ -168,14 +168,14 @@ PG_HD V3 mink_ls(const Mink& md, const Shape& s, V3 d) {
   return support_core(s, n) + n * s.margin;
 }
 PG_HD V3 mink_support0(const Mink& md, V3 d) { return mink_ls(md, *md.s0, d); }
-PG_HD V3 mink_support1(const Mink& md, V3 d) { return mul(md.to0, mink_ls(md, *md.s1, mul(md.to1, d))) + md.to0_o; }
+PG_HDN V3 mink_support1(const Mink& md, V3 d) { return mul(md.to0, mink_ls(md, *md.s1, mul(md.to1, d))) + md.to0_o; }
 PG_HD V3 mink_support(const Mink& md, V3 d) { return mink_support0(md, d) - mink_support1(md, -d); }
 PG_HD M3 mulTM(const M3& a, const M3& b) {
   M3 r;
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r(i, j) = dot(a.col(i), b.col(j));
   return r;
 }
-PG_HD void mink_init(Mink& md, const Shape& s0, const Xf& x0, const Shape& s1, const Xf& x1, bool margins) {
+PG_HDN void mink_init(Mink& md, const Shape& s0, const Xf& x0, const Shape& s1, const Xf& x1, bool margins) {
   md.s0 = &s0; md.s1 = &s1;
   md.to1 = mulTM(x1.R, x0.R); md.to0 = mulTM(x0.R, x1.R); md.to0_o = mulT(x0.R, x1.o - x0.o);
   md.margins = margins;
@@ -203,7 +203,7 @@ struct Gjk2 {
 PG_HD double det3(V3 a, V3 b, V3 c) {
   return a.y * b.z * c.x + a.z * b.x * c.y - a.x * b.z * c.y - a.y * b.x * c.z + a.x * b.y * c.z - a.z * b.y * c.x;
 }
-PG_HD void g_support(const Gjk2& g, V3 d, SV& sv) { sv.d = vdiv(d, len(d)); sv.w = mink_support(*g.md, sv.d); }
+PG_HDN void g_support(const Gjk2& g, V3 d, SV& sv) { sv.d = vdiv(d, len(d)); sv.w = mink_support(*g.md, sv.d); }
 PG_HD void g_remove(Gjk2& g, GSimplex& s) { g.free_[g.nfree++] = s.c[--s.rank]; }
 PG_HD void g_append(Gjk2& g, GSimplex& s, V3 v) { s.p[s.rank] = 0; s.c[s.rank] = g.free_[--g.nfree]; g_support(g, v, g.sv[s.c[s.rank]]); s.rank++; }
 
@@ -355,7 +355,7 @@ PG_HD bool enclose_origin(Gjk2& g, GSimplex& s) {       // callers only reach th
 
 struct Epa {
   SV* sv; Face* fc; Scratch* sc;
-  short hull_root, stock_root; int hull_count, nextsv;
+  short hull_root, stock_root; int hull_count, nextsv, fresh;
   int status;            // 0 valid .. 9 failed (7 accuracy reached, 6 out of vertices, 8 fallback)
   V3 normal; double depth;
   int rrank; unsigned char rc[3]; double rp[3];
@@ -377,7 +377,7 @@ PG_HD void fl_remove(Epa& e, short& root, short f) {
 PG_HD void epa_bind(Epa& e, short fa, int ea, short fb, int eb) {
   e.fc[fa].e[ea] = (unsigned char)eb; e.fc[fa].f[ea] = fb; e.fc[fb].e[eb] = (unsigned char)ea; e.fc[fb].f[eb] = fa;
 }
-PG_HD bool edge_dist(const Epa& e, const Face& face, int ia, int ib, double& dist) {
+PG_HDN bool edge_dist(const Epa& e, const Face& face, int ia, int ib, double& dist) {
   V3 a = e.sv[ia].w, b = e.sv[ib].w;
   V3 ba = b - a, n_ab = cross(ba, face.n);
   if (dot(a, n_ab) < 0) {
@@ -390,9 +390,13 @@ PG_HD bool edge_dist(const Epa& e, const Face& face, int ia, int ib, double& dis
   return false;
 }
 PG_HDN short epa_newface(Epa& e, int a, int b, int c, bool forced) {
-  if (e.stock_root >= 0) {
-    short f = e.stock_root;
-    fl_remove(e, e.stock_root, f); fl_append(e, e.hull_root, f); e.hull_count++;
+  // free faces: the list of returned ones first (most recently returned on top), then the never-used slots in index
+  // order -- the same pop order as a stock list pre-filled with all 256 slots, without writing 256 links per query
+  if (e.stock_root >= 0 || e.fresh < EPA_MAXF) {
+    short f;
+    if (e.stock_root >= 0) { f = e.stock_root; fl_remove(e, e.stock_root, f); }
+    else f = (short)e.fresh++;
+    fl_append(e, e.hull_root, f); e.hull_count++;
     Face& F = e.fc[f];
     F.pass = 0; F.c[0] = (unsigned char)a; F.c[1] = (unsigned char)b; F.c[2] = (unsigned char)c;
     F.n = cross(e.sv[b].w - e.sv[a].w, e.sv[c].w - e.sv[a].w);
@@ -410,7 +414,7 @@ PG_HDN short epa_newface(Epa& e, int a, int b, int c, bool forced) {
   e.status = EPA_OUTOFFACES;
   return -1;
 }
-PG_HD short epa_findbest(const Epa& e) {
+PG_HDN short epa_findbest(const Epa& e) {
   short minf = e.hull_root; double mind = e.fc[minf].d * e.fc[minf].d;
   for (short f = e.fc[minf].next; f >= 0; f = e.fc[f].next) { double sq = e.fc[f].d * e.fc[f].d; if (sq < mind) { minf = f; mind = sq; } }
   return minf;
@@ -462,9 +466,7 @@ PG_HDN int epa_evaluate(Epa& e, Gjk2& g, Scratch& sc, V3 guess) {
   GSimplex& s = g.sx[g.current];
   e.status = EPA_FAILED;
   if (s.rank > 1 && enclose_origin(g, s)) {
-    // all faces to the stock list, first slot on top
-    e.hull_root = -1; e.stock_root = -1; e.hull_count = 0;
-    for (int i = 0; i < EPA_MAXF; i++) fl_append(e, e.stock_root, (short)(EPA_MAXF - i - 1));
+    e.hull_root = -1; e.stock_root = -1; e.hull_count = 0; e.fresh = 0;
     e.status = EPA_VALID; e.nextsv = 0;
     const SV* sv = e.sv;
     if (det3(sv[s.c[0]].w - sv[s.c[3]].w, sv[s.c[1]].w - sv[s.c[3]].w, sv[s.c[2]].w - sv[s.c[3]].w) < 0) {

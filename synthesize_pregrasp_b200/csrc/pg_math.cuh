@@ -5,10 +5,10 @@
 
 #if defined(__CUDACC__)
 #define PG_HD __host__ __device__ __forceinline__
-#define PG_HDN __host__ __device__ __noinline__
+#define PG_HDN static __host__ __device__ __noinline__
 #else
 #define PG_HD inline
-#define PG_HDN
+#define PG_HDN static
 #endif
 
 namespace pg {

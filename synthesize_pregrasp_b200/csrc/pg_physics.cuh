@@ -18,6 +18,9 @@
 
 namespace pg {
 
+#if defined(__CUDACC__)
+__shared__ double pg_hull_sm[MAX_HULL * 3];       // hull vertices of the env, staged once per CTA (hull kernel only)
+#endif
 enum { B_OBJ = MAX_STATICS, B_TIP0 = MAX_STATICS + 1, B_TIP1 = MAX_STATICS + 2, NBODY = MAX_STATICS + 3 };
 enum { MAXM = 12, MAXPTS = 24 };
 
@@ -482,7 +485,12 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
       cvx::Shape sh[2];
       for (int side = 0; side < 2; side++) {
         int b = side ? m.b : m.a;
-        sh[side].hull = (b == B_OBJ); sh[side].half = bv[b].half; sh[side].verts = E.hull; sh[side].nverts = E.n_hull; sh[side].margin = E.obj_margin;
+        sh[side].hull = (b == B_OBJ); sh[side].half = bv[b].half; sh[side].nverts = E.n_hull; sh[side].margin = E.obj_margin;
+#if defined(__CUDA_ARCH__)
+        sh[side].verts = pg_hull_sm;       // every support query walks all vertices: 30 % of the hull kernel's stalls were these loads from L2
+#else
+        sh[side].verts = E.hull;
+#endif
       }
       V3 n, pb; double dist;
       if (cvx::closest_points(sh[0], bv[m.a].pos, bv[m.a].R, sh[1], bv[m.b].pos, bv[m.b].R, m.breaking, scratch, n, pb, dist))

@@ -6,38 +6,13 @@
 // latency on every row; a thread per rollout keeps all 32 lanes busy with independent rollouts and the only
 // divergence is the per-rollout row count.  HBM sees u + noise in and pose/fins/metric out; everything else
 // (bodies, manifolds, solver rows) lives in registers and thread-local memory for the whole rollout.
-#define PG_BLOCK_THREADS 64
-#include <cstdlib>
-#include "pg_internal.h"
-#include "pg_rollout.cuh"
+#include "pg_rollout_kernel.cuh"
 
 namespace pg {
 
-#define RK_THREADS PG_BLOCK_THREADS
-#ifndef RK_MINBLOCKS
-#define RK_MINBLOCKS 7
-#endif
-// SHAPE: the object's collision shape; box objects never instantiate the GJK / polytope code (and its ~21 KB of
-// per-thread scratch), hull objects (plate) get their own kernel
-template <int SHAPE>
-__global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const EnvDev* __restrict__ env, const double* __restrict__ u,
-                                                      const float* __restrict__ noise, int K, int N,
-                                                      const int* __restrict__ path, double max_force,
-                                                      double* __restrict__ pose, double* __restrict__ fins,
-                                                      double* __restrict__ metric, double* __restrict__ trace,
-                                                      int* __restrict__ iters) {
-  // grid-stride over the batch: the host may launch fewer CTAs than K/64 to cap how many rollouts are resident
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
-    RolloutOut out;
-    out.pose = pose + (size_t)k * N * 7;
-    out.fins = fins + (size_t)k * N * NFING * 3;
-    out.metric = metric ? metric + k : nullptr;
-    out.trace = trace ? trace + (size_t)k * N * SKIP * 7 : nullptr;
-    out.iters = iters ? iters + (size_t)k * N * SKIP : nullptr;
-    out.settle_iters = nullptr;
-    rollout_one<SHAPE>(*env, u, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path, max_force, 1, out, nullptr, 0);   // solver slice: dynamic shared memory, see PG_SM
-  }
-}
+// defined in pg_rollout_hull.cu (compiled without FMA contraction: GJK / polytope decisions are rounding-sensitive)
+void launch_rollout_hull(int blocks, int threads, size_t smem, cudaStream_t st, const EnvDev* env, const double* u, const float* noise,
+                         int K, int N, const int* path, double max_force, double* pose, double* fins, double* metric, double* trace, int* iters);
 
 int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
                    double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st) {
@@ -55,7 +30,7 @@ int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N
   const size_t smem = SM_DOUBLES * RK_THREADS * sizeof(double);
   if (blocks > ctas_per_sm * n_sm) blocks = ctas_per_sm * n_sm;
   if (env->host_env.obj_shape != SHAPE_BOX)
-    rollout_kernel<SHAPE_HULL><<<blocks, threads, smem, st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
+    launch_rollout_hull(blocks, threads, smem, st, env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
   else
     rollout_kernel<SHAPE_BOX><<<blocks, threads, smem, st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
   count_launch();

@@ -1,0 +1,41 @@
+// The rollout kernel template (one thread per rollout); instantiated for box objects in pg_rollout.cu and for hull objects
+// in pg_rollout_hull.cu -- two translation units because they are compiled with different floating-point contraction.
+#pragma once
+#define PG_BLOCK_THREADS 64
+#include <cstdlib>
+#include "pg_internal.h"
+#include "pg_rollout.cuh"
+
+namespace pg {
+
+#define RK_THREADS PG_BLOCK_THREADS
+#ifndef RK_MINBLOCKS
+#define RK_MINBLOCKS 7
+#endif
+// SHAPE: the object's collision shape; box objects never instantiate the GJK / polytope code (and its ~21 KB of
+// per-thread scratch), hull objects (plate) get their own kernel
+template <int SHAPE>
+__global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const EnvDev* __restrict__ env, const double* __restrict__ u,
+                                                      const float* __restrict__ noise, int K, int N,
+                                                      const int* __restrict__ path, double max_force,
+                                                      double* __restrict__ pose, double* __restrict__ fins,
+                                                      double* __restrict__ metric, double* __restrict__ trace,
+                                                      int* __restrict__ iters) {
+  if (SHAPE == SHAPE_HULL) {
+    for (int i = threadIdx.x; i < 3 * env->n_hull; i += blockDim.x) pg_hull_sm[i] = env->hull[i];
+    __syncthreads();
+  }
+  // grid-stride over the batch: the host may launch fewer CTAs than K/64 to cap how many rollouts are resident
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+    RolloutOut out;
+    out.pose = pose + (size_t)k * N * 7;
+    out.fins = fins + (size_t)k * N * NFING * 3;
+    out.metric = metric ? metric + k : nullptr;
+    out.trace = trace ? trace + (size_t)k * N * SKIP * 7 : nullptr;
+    out.iters = iters ? iters + (size_t)k * N * SKIP : nullptr;
+    out.settle_iters = nullptr;
+    rollout_one<SHAPE>(*env, u, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path, max_force, 1, out, nullptr, 0);   // solver slice: dynamic shared memory, see PG_SM
+  }
+}
+
+}  // namespace pg
