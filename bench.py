@@ -243,11 +243,20 @@ def main():
     F64_PEAK_TF = 148 * 64 * 2 * 1.965e9 / 1e12     # nominal DFMA rate (half the fp32 lanes)
     bytes_phys = K * (N_STEPS * D * 4 + N_STEPS * (7 + 6) * 8 + 8) + N_STEPS * D * 8
     ach_hbm = bytes_phys / (phys_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_kernel launch at K = 65536 (ncu, profiles/r1d_sections_*.csv);
+    # scaled linearly in K for other batch sizes of the same workload, null for workloads that were not captured
+    NCU_TRAFFIC_K65536 = {"bookshelf": 4723434166528 + 788487916288, "plate": 1676992608256 + 884871619072}
+    traffic = NCU_TRAFFIC_K65536.get(wl["env"])
+    traffic = None if traffic is None else traffic * (K / 65536.0)
     roof = {"kernel": "rollout_kernel (physics, %.0f%% of the step)" % (100 * phys_ms / (phys_ms + cost_ms)), "bound": "hbm",
-            "achieved": ach_hbm, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach_hbm / peaks["hbm"], "traffic": None,
+            "achieved": ach_hbm, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach_hbm / peaks["hbm"], "traffic": traffic,
             "peak_source": peaks["src"],
-            "note": "algorithmic HBM bytes are ~400 B per rollout-step, so this fraction is tiny by construction: the kernel is "
-                    "fp64 issue/latency bound (roofline_fp64); ncu dram traffic of the K=8192 capture is in profiles/"}
+            "actual_dram_gbs": None if traffic is None else traffic / (phys_ms * 1e-3) / 1e9,
+            "note": "algorithmic HBM bytes are ~400 B per rollout-step (u, noise in; pose, fins, metric out), so frac is tiny by "
+                    "construction.  The measured traffic is 5 orders of magnitude above it: the per-rollout solver rows (2-3 KB, "
+                    "thread-local memory) of all 66k resident rollouts exceed the 126 MB L2 and are re-read from HBM on every "
+                    "Gauss-Seidel iteration (L2 hit 24 %), which puts the kernel at ~60 % of HBM bandwidth with latency-bound "
+                    "warps (profiles/README.md).  Keeping those rows on chip is the next optimisation."}
     ach64 = FLOP_PER_SUBSTEP * substeps * K / (phys_ms * 1e-3) / 1e12
     roof64 = {"kernel": "rollout_kernel", "bound": "fp64-issue", "achieved": ach64, "peak": F64_PEAK_TF, "unit": "TFLOP/s",
               "frac": ach64 / F64_PEAK_TF, "peak_source": "nominal 148 SM x 64 DFMA/clk x 1.965 GHz"}
