@@ -173,6 +173,8 @@ struct Params {
   double aabb_margin = 0.02;      // contact threshold added to AABBs
   double max_coord_vel = 100.0;   // btMultiBody::m_maxCoordinateVelocity
   int pair_order_mode = -1;       // -1: by object type; 0: box-object order; 1: compound-object order (see collide)
+  double tight_pad = 0.0;         // debugging: slack added to the tight-AABB test of compound children
+  int order_step_min = 0;         // debugging: manifold_order3 applies from this step on
   int manifold_reverse = 0;       // debugging: reverse the final manifold order
   int manifold_order3 = 0;        // debugging: explicit order (digits, creation indices) when exactly 3 manifolds are solved
   int manifold_order = 0;         // 0: emulate quickSort of dispatcher order; k>=1: (k-1)-th permutation of creation order
@@ -614,8 +616,8 @@ static bool aabb_overlap(const Body& a, const Body& b) {
 static bool pair_overlap(const World& w, const Body& a, const Body& b) {
   if (!aabb_overlap(a, b)) return false;
   if (a.compound || b.compound) {
-    double ea = w.P.aabb_margin + (a.shape.in_compound ? g_compound_margin : 0.0);
-    double eb = w.P.aabb_margin + (b.shape.in_compound ? g_compound_margin : 0.0);
+    double ea = w.P.aabb_margin + (a.shape.in_compound ? g_compound_margin : 0.0) - 0.5 * w.P.tight_pad;
+    double eb = w.P.aabb_margin + (b.shape.in_compound ? g_compound_margin : 0.0) - 0.5 * w.P.tight_pad;
     for (int k = 0; k < 3; k++)
       if (a.aabb_lo[k] + ea > b.aabb_hi[k] - eb || a.aabb_hi[k] - ea < b.aabb_lo[k] + eb) return false;
   }
@@ -980,7 +982,7 @@ static void solve(World& w) {
     std::vector<int> mlist;
     for (auto& o : order) if (o.first == isl || isl == -2) mlist.push_back(o.second);
     int nd3 = 0; for (int c = P.manifold_order3; c > 0; c /= 10) nd3++;
-    if (P.manifold_order3 > 0 && (int)mlist.size() == nd3 - 1) {
+    if (P.manifold_order3 > 0 && (int)mlist.size() == nd3 - 1 && w.step_count >= P.order_step_min) {
       std::sort(mlist.begin(), mlist.end());
       std::vector<int> src = mlist; int code = P.manifold_order3;
       for (int k = nd3 - 2; k >= 0; k--) { mlist[k] = src[code % 10]; code /= 10; }
@@ -1134,8 +1136,8 @@ void pgo_set_param(void* h, const char* name, double v) {
   Params& P = ((World*)h)->P;
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
-  S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(default_max_impulse) S(debug)
+  S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(default_max_impulse) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }

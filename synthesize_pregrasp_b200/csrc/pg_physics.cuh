@@ -939,7 +939,7 @@ PG_HD void integrate(const EnvDev& E, Sim& S) {
 }
 
 template <int SHAPE>
-PG_HD void substep(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, double* sm, int ss) {
+PG_HDN void substep(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, double* sm, int ss) {
   collide<SHAPE>(E, S, statR);
   apply_external(E, S);
   solve(E, S, statR, rs, sm, ss);
