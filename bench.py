@@ -24,6 +24,7 @@ WORKLOADS = {   # BASELINE.json configs: env, max force, K per GPU
     "foodbox_K65536": dict(env="foodbox", force=20.0, K=65536),
     "plate_K65536": dict(env="plate", force=20.0, K=65536),        # configs[0]'s task at the headline batch size
     "plate_K360": dict(env="plate", force=20.0, K=360),            # configs[0] as the reference runs it: 12 workers x 30 (model_optimize.py:77)
+    "waterbottle_K65536": dict(env="waterbottle", force=20.0, K=65536),   # SURVEY 8(d) config 4, per-GPU share
 }
 SIGMA, KAPPA, ALPHA, N_STEPS, D = 0.8, 5.0, 1.0, 2, 48
 

@@ -277,3 +277,27 @@ def test_two_env_handles_on_two_streams(EN):
     torch.cuda.synchronize()
     for a, b in zip(ref, outs):
         assert torch.equal(a, b)
+
+
+def test_csg_node_scores_match_oracle(EN):
+    """generate_csg.node_scores: all (node x sample) score evaluations in one pg_score launch vs the oracle network."""
+    from oracle import scorenet as SN
+    from synthesize_pregrasp_b200 import generate_csg as G
+    from synthesize_pregrasp_b200.envspec import make_spec
+    spec = make_spec("plate")
+    eng = EN.RolloutEngine(spec, device=0)
+    rng = np.random.RandomState(11)
+    cloud = spec.cloud[:1024].astype(np.float32)
+    df = (cloud[:, 2] + 0.1).astype(np.float32)                 # generate_csg.py:47
+    regions = list(range(6))
+    samples = [cloud[rng.randint(0, 1024, size=G.NUM_SAMPLES)] + 0.002 * rng.randn(G.NUM_SAMPLES, 3).astype(np.float32) for _ in regions]
+    nodes = G.all_ordered_nodes(regions)
+    got = G.node_scores(eng, cloud, df, samples, nodes)
+    w = oracle_weights()
+    for n in (0, 7, len(nodes) - 1):
+        i, j = nodes[n]
+        ref = np.mean([SN.score_logit(w, cloud.astype(np.float64), df.astype(np.float64), np.r_[samples[i][t], samples[j][t]].astype(np.float64))
+                       for t in range(G.NUM_SAMPLES)])
+        assert abs(got[n] - ref) <= 2e-5 * max(1.0, abs(ref)), (n, got[n], ref)
+    table, ids, _, _ = G.select_paths(nodes[:10], got[:10], nodes, got)
+    assert ids.shape == (10, 2) and table.shape[1] == 2

@@ -184,3 +184,35 @@ def test_product_kernel_logic_on_host_matches_oracle():
         assert np.median(d) <= 1e-8, (env, np.median(d))
         for j in range(N):
             np.testing.assert_allclose(fins[0, j], rs[j]["cur_pos"], rtol=0, atol=1e-12)
+
+
+def test_csg_path_selection_matches_bruteforce():
+    """generate_csg.select_paths (reference: neurals/scripts/generate_csg.py:136-180) vs an independent enumeration."""
+    import itertools
+    from synthesize_pregrasp_b200 import generate_csg as G
+    rng = np.random.RandomState(3)
+    regions = [1, 2, 3, 5, 8]
+    nodes = G.all_ordered_nodes(regions)
+    assert len(nodes) == 20 and nodes[0] == (1, 2) and nodes[-1] == (8, 5)
+    all_scores = rng.randn(len(nodes))
+    init_idx = [i for i, n in enumerate(nodes) if n[0] in (1, 2, 3) and n[1] in (1, 2, 3)]
+    init_nodes = [nodes[i] for i in init_idx]
+    init_scores = rng.randn(len(init_nodes))
+    table, ids, sorted_paths, sorted_scores = G.select_paths(init_nodes, init_scores, nodes, all_scores, k=2, top=10)
+    brute = []
+    for (a, sa), (b, sb) in itertools.product(zip(init_nodes, init_scores), zip(nodes, all_scores)):
+        if b[0] == a[0] or b[1] == a[1]:
+            brute.append((sa + sb, a, b))
+    brute.sort(key=lambda t: t[0])
+    assert len(brute) == len(sorted_paths)
+    np.testing.assert_allclose(sorted_scores, [t[0] for t in brute], rtol=0, atol=1e-15)
+    for p, t in zip(sorted_paths[:10], brute[:10]):
+        assert tuple(p[0]) == t[1] and tuple(p[1]) == t[2]
+    assert ids.shape == (10, 2)
+    for row, p in zip(ids, sorted_paths[:10]):                 # the id table indexes back to the chosen nodes
+        assert [tuple(table[i]) for i in row] == [tuple(n) for n in p]
+    # three-node paths: every consecutive pair keeps one finger's region
+    _, _, sp3, _ = G.select_paths(init_nodes, init_scores, nodes, all_scores, k=3, top=5)
+    for p in sp3[:50]:
+        for a, b in zip(p[:-1], p[1:]):
+            assert a[0] == b[0] or a[1] == b[1]
