@@ -2,6 +2,7 @@
 the host logic, and that the C-ABI library loads and exports every symbol include/pregrasp_b200.h declares."""
 import ctypes as C
 import os
+import sys
 import re
 import subprocess
 
@@ -216,3 +217,19 @@ def test_csg_path_selection_matches_bruteforce():
     for p in sp3[:50]:
         for a, b in zip(p[:-1], p[1:]):
             assert a[0] == b[0] or a[1] == b[1]
+
+
+def test_kernel_logic_is_clean_under_address_and_ub_sanitizers():
+    """compute-sanitizer is not available on the GPU pool, so the per-thread kernel code (box-box, GJK, polytope pools,
+    explicit stacks, manifold arrays, solver rows) is compiled for the host with -fsanitize=address,undefined and run on
+    random rollouts of all seven envs."""
+    so = os.path.join(ROOT, "tests", "hostsim", "libpg_hostsim_asan.so")
+    subprocess.check_call(["g++", "-O1", "-g", "-fPIC", "-std=c++17", "-ffp-contract=off", "-fsanitize=address,undefined",
+                           "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined", "-shared", "-include", "cstdio", "-o", so,
+                           os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")])
+    asan = subprocess.check_output(["g++", "-print-file-name=libasan.so"]).decode().strip()
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "hostsim", "asan_driver.py"), so], env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count(" ok") == 7, out.stdout
