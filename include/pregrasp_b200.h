@@ -101,6 +101,12 @@ int pg_rollout_host(PgEnv* env, const double* u_host, const float* noise_host, i
                     const int32_t* path_host, double max_force, double* J_host, double* metric_host,
                     double* trace_host);
 
+/* Q independent MPPI problems in one launch.  Replaces the serial outer loops of model_optimize.py:74-117 (one optimiser per
+   contact-state path and per repetition): rollout k uses u[prob[k]] and paths[prob[k]].  Device: u [Q,N,48] f64, noise [K,N,48] f32,
+   prob [K] i32, J [K], metric [K] or NULL; host: paths [Q,N] i32.  The prob values must lie in [0,Q) (not checked on the device). */
+int pg_rollout_multi(PgEnv* env, const double* u_dev, const float* noise_dev, int K, int N, int Q, const int32_t* prob_dev,
+                     const int32_t* paths_host, double max_force, double* J_dev, double* metric_dev, void* stream);
+
 /* the two stages of pg_rollout, exposed for tests and profiling */
 int pg_physics(PgEnv* env, const double* u_dev, const float* noise_dev, int K, int N, const int32_t* path_host,
                double max_force, double* pose_dev /*[K,N,7]*/, double* fins_dev /*[K,N,2,3]*/,

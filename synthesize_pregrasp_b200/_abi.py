@@ -166,6 +166,7 @@ def lib():
     L.pg_env_create.argtypes = [C.POINTER(PgEnvSpec), i32, C.POINTER(vp)]
     L.pg_env_destroy.argtypes = [vp]
     L.pg_rollout.argtypes = [vp, vp, vp, i32, i32, _IP, f64, vp, vp, vp, vp]
+    L.pg_rollout_multi.argtypes = [vp, vp, vp, i32, i32, i32, vp, _IP, f64, vp, vp, vp]
     L.pg_rollout_host.argtypes = [vp, _DP, _FP, i32, i32, _IP, f64, _DP, _DP, _DP]
     L.pg_physics.argtypes = [vp, vp, vp, i32, i32, _IP, f64, vp, vp, vp, vp, vp, vp]
     L.pg_cost.argtypes = [vp, vp, vp, i32, vp, vp]
@@ -174,14 +175,14 @@ def lib():
     L.pg_mppi_merge_apply.argtypes = [_DP, i32, i32, i32, f64, f64, _DP]
     L.pg_dyn_feasible_simple.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.pg_dyn_sweep_simple.argtypes = [vp, vp, i32, f64, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp]
-    for f in ("pg_env_create", "pg_env_destroy", "pg_rollout", "pg_rollout_host", "pg_physics", "pg_cost", "pg_score",
+    for f in ("pg_env_create", "pg_env_destroy", "pg_rollout", "pg_rollout_multi", "pg_rollout_host", "pg_physics", "pg_cost", "pg_score",
               "pg_mppi_update", "pg_mppi_merge_apply", "pg_dyn_feasible_simple", "pg_dyn_sweep_simple"):
         getattr(L, f).restype = C.c_int
     _lib = L
     return L
 
 
-EXPORTS = ("pg_last_error", "pg_version", "pg_env_create", "pg_env_destroy", "pg_rollout", "pg_rollout_host", "pg_physics",
+EXPORTS = ("pg_last_error", "pg_version", "pg_env_create", "pg_env_destroy", "pg_rollout", "pg_rollout_multi", "pg_rollout_host", "pg_physics",
            "pg_cost", "pg_score", "pg_mppi_update", "pg_mppi_merge_apply", "pg_dyn_feasible_simple", "pg_dyn_sweep_simple",
            "pg_launch_count")
 

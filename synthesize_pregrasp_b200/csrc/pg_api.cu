@@ -143,7 +143,7 @@ static int ensure_scratch(PgEnv* e, size_t evals) {
   PG_CUDA(cudaMalloc(&e->fins, evals * 6 * sizeof(double)));
   PG_CUDA(cudaMalloc(&e->logit, evals * sizeof(float)));
   PG_CUDA(cudaMalloc(&e->latent, evals * LAT * sizeof(float)));
-  if (!e->path_dev) PG_CUDA(cudaMalloc(&e->path_dev, 64 * sizeof(int)));
+  if (!e->path_dev) { PG_CUDA(cudaMalloc(&e->path_dev, 64 * sizeof(int))); e->cap_path = 64; }
   e->cap_evals = evals;
   return PG_OK;
 }
@@ -196,6 +196,30 @@ extern "C" int pg_rollout(PgEnv* e, const double* u_dev, const float* noise_dev,
   if (rc) return rc;
   PG_CUDA(cudaMemcpyAsync(e->path_dev, path_host, N * sizeof(int), cudaMemcpyHostToDevice, st));
   rc = launch_physics(e, u_dev, noise_dev, K, N, e->path_dev, max_force, e->pose, e->fins, metric_dev, trace_dev, nullptr, st);
+  if (rc) return rc;
+  rc = launch_cost(e, e->pose, e->fins, K * N, e->latent, e->logit, st);
+  if (rc) return rc;
+  return launch_accumulate_cost(e->logit, K, N, J_dev, st);
+}
+
+// model_optimize.py:74-117 runs one MPPI problem per (contact-state path, repetition) one after the other; they are
+// independent, so Q of them can share every launch: rollout k belongs to problem prob[k]
+extern "C" int pg_rollout_multi(PgEnv* e, const double* u_dev, const float* noise_dev, int K, int N, int Q, const int32_t* prob_dev,
+                                const int32_t* paths_host, double max_force, double* J_dev, double* metric_dev, void* stream) {
+  if (!e || !u_dev || !paths_host || !prob_dev || !J_dev || K <= 0 || N <= 0 || N > 32 || Q <= 0) { set_error("pg_rollout_multi: bad arguments"); return PG_ERR_INVALID; }
+  for (int i = 0; i < Q * N; i++) if (paths_host[i] < 0 || paths_host[i] >= e->host_env.n_states) { set_error("pg_rollout_multi: path state out of range"); return PG_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  PG_CUDA(cudaSetDevice(e->device));
+  int rc = ensure_scratch(e, (size_t)K * N);
+  if (rc) return rc;
+  if (e->cap_path < (size_t)Q * N) {
+    PG_CUDA(cudaStreamSynchronize(st));
+    cudaFree(e->path_dev); e->path_dev = nullptr; e->cap_path = 0;
+    PG_CUDA(cudaMalloc(&e->path_dev, (size_t)Q * N * sizeof(int)));
+    e->cap_path = (size_t)Q * N;
+  }
+  PG_CUDA(cudaMemcpyAsync(e->path_dev, paths_host, (size_t)Q * N * sizeof(int), cudaMemcpyHostToDevice, st));
+  rc = launch_physics(e, u_dev, noise_dev, K, N, e->path_dev, max_force, e->pose, e->fins, metric_dev, nullptr, nullptr, st, prob_dev);
   if (rc) return rc;
   rc = launch_cost(e, e->pose, e->fins, K * N, e->latent, e->logit, st);
   if (rc) return rc;

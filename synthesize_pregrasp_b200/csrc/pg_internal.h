@@ -48,7 +48,7 @@ struct PgEnv {
   double *pose, *fins;           // [K,N,7], [K,N,2,3]
   float* logit;                  // [K*N]
   float* latent;                 // [K*N,26]
-  int* path_dev;
+  int* path_dev; size_t cap_path;
   size_t cap_evals;
   double *u_stage; float* noise_stage; double *J_stage, *metric_stage, *trace_stage;   // pg_rollout_host staging
   size_t cap_stage_K, cap_stage_trace;
@@ -60,7 +60,8 @@ int cuda_fail(cudaError_t e, const char* what);
 void count_launch();
 #define PG_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return pg::cuda_fail(_e, #x); } while (0)
 int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
-                   double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st);
+                   double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st,
+                   const int* prob_dev = nullptr);
 int launch_cost(PgEnv* env, const double* pose, const double* fins, int B, float* latent, float* logit, cudaStream_t st);
 int launch_score(PgEnv* env, const float* pts, const float* df, const uint8_t* mask, const float* grasp, int B, int P,
                  float* latent, float* logit, cudaStream_t st);

@@ -12,10 +12,11 @@ namespace pg {
 
 // defined in pg_rollout_hull.cu (compiled without FMA contraction: GJK / polytope decisions are rounding-sensitive)
 void launch_rollout_hull(int blocks, int threads, size_t smem, cudaStream_t st, const EnvDev* env, const double* u, const float* noise,
-                         int K, int N, const int* path, double max_force, double* pose, double* fins, double* metric, double* trace, int* iters);
+                         int K, int N, const int* path, double max_force, double* pose, double* fins, double* metric, double* trace, int* iters,
+                         const int* prob);
 
 int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
-                   double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st) {
+                   double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st, const int* prob_dev) {
   const int threads = RK_THREADS;
   int blocks = (K + threads - 1) / threads;
   // Resident CTAs per SM: the solver rows of all resident rollouts (2-3 KB each) are re-read every Gauss-Seidel
@@ -30,9 +31,9 @@ int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N
   const size_t smem = SM_DOUBLES * RK_THREADS * sizeof(double);
   if (blocks > ctas_per_sm * n_sm) blocks = ctas_per_sm * n_sm;
   if (env->host_env.obj_shape != SHAPE_BOX)
-    launch_rollout_hull(blocks, threads, smem, st, env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
+    launch_rollout_hull(blocks, threads, smem, st, env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters, prob_dev);
   else
-    rollout_kernel<SHAPE_BOX><<<blocks, threads, smem, st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters);
+    rollout_kernel<SHAPE_BOX><<<blocks, threads, smem, st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters, prob_dev);
   count_launch();
   PG_CUDA(cudaGetLastError());
   return PG_OK;

@@ -7,8 +7,9 @@
 namespace pg {
 
 void launch_rollout_hull(int blocks, int threads, size_t smem, cudaStream_t st, const EnvDev* env, const double* u, const float* noise,
-                         int K, int N, const int* path, double max_force, double* pose, double* fins, double* metric, double* trace, int* iters) {
-  rollout_kernel<SHAPE_HULL><<<blocks, threads, smem, st>>>(env, u, noise, K, N, path, max_force, pose, fins, metric, trace, iters);
+                         int K, int N, const int* path, double max_force, double* pose, double* fins, double* metric, double* trace, int* iters,
+                         const int* prob) {
+  rollout_kernel<SHAPE_HULL><<<blocks, threads, smem, st>>>(env, u, noise, K, N, path, max_force, pose, fins, metric, trace, iters, prob);
 }
 
 }  // namespace pg

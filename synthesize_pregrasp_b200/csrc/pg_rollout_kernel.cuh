@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const
                                                       const int* __restrict__ path, double max_force,
                                                       double* __restrict__ pose, double* __restrict__ fins,
                                                       double* __restrict__ metric, double* __restrict__ trace,
-                                                      int* __restrict__ iters) {
+                                                      int* __restrict__ iters, const int* __restrict__ prob) {
   if (SHAPE == SHAPE_HULL) {
     for (int i = threadIdx.x; i < 3 * env->n_hull; i += blockDim.x) pg_hull_sm[i] = env->hull[i];
     __syncthreads();
@@ -34,7 +34,9 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const
     out.trace = trace ? trace + (size_t)k * N * SKIP * 7 : nullptr;
     out.iters = iters ? iters + (size_t)k * N * SKIP : nullptr;
     out.settle_iters = nullptr;
-    rollout_one<SHAPE>(*env, u, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path, max_force, 1, out, nullptr, 0);   // solver slice: dynamic shared memory, see PG_SM
+    // several independent MPPI problems may share a launch: rollout k then uses the controls and the path of problem prob[k]
+    const int q = prob ? prob[k] : 0;
+    rollout_one<SHAPE>(*env, u + (size_t)q * N * ADIM, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path + (size_t)q * N, max_force, 1, out, nullptr, 0);   // solver slice: dynamic shared memory, see PG_SM
   }
 }
 

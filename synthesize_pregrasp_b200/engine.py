@@ -94,6 +94,25 @@ class RolloutEngine:
             out.append(trace)
         return out[0] if len(out) == 1 else tuple(out)
 
+    def rollout_multi(self, u, noise, prob, paths, max_force, want_metric=False):
+        """Q independent MPPI problems in one launch (model_optimize.py:74-117 runs them one after the other).
+        u [Q,N,48] f64 CUDA tensor, noise [K,N,48] f32 CUDA tensor, prob [K] int32 CUDA tensor (problem of each rollout),
+        paths [Q,N] contact states.  -> J [K] (+ metric [K])."""
+        with torch.cuda.device(self.device):
+            assert u.is_cuda and u.dtype == torch.float64 and u.is_contiguous() and u.dim() == 3
+            assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous()
+            assert prob.is_cuda and prob.dtype == torch.int32 and prob.is_contiguous()
+            Q, N = u.shape[0], u.shape[1]
+            K = noise.shape[0]
+            assert tuple(noise.shape[1:]) == (N, ACTION_DIM) and prob.shape[0] == K
+            p = np.ascontiguousarray(np.asarray(paths, np.int32)[:, :N])
+            assert p.shape == (Q, N)
+            J = torch.empty(K, dtype=torch.float64, device=self._dev())
+            metric = torch.empty(K, dtype=torch.float64, device=self._dev()) if want_metric else None
+            _abi.check(self.lib.pg_rollout_multi(self.handle, _ptr(u), _ptr(noise), K, N, Q, _ptr(prob), p.ctypes.data_as(_abi._IP),
+                                                 float(max_force), _ptr(J), _ptr(metric), _stream()))
+        return (J, metric) if want_metric else J
+
     def rollout_host(self, u, noise, path, max_force, K=None, want_metric=False, want_trace=False):
         """Host-buffer form (numpy in, numpy out; H2D/D2H inside) -- the plugin-facing call."""
         u = np.ascontiguousarray(u, np.float64)

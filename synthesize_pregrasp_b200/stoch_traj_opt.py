@@ -94,3 +94,56 @@ class StochTrajOptimizer:
 
     def render_traj(self, u, replay_times=10):
         raise NotImplementedError("rendering is out of scope of the GPU rollout path (SURVEY.md section 2, row 17)")
+
+
+class MultiStochTrajOptimizer:
+    """Q independent StochTrajOptimizer problems advanced in lock-step, one launch per MPPI iteration.
+
+    model_optimize.py:74-117 builds one optimiser per contact-state path (up to 10) and per repetition (`--runs`, 3) and runs
+    them one after the other, each with only Num_processes*Traj_per_process = 360 samples -- far too few to fill a GPU with
+    one thread per rollout.  The problems share the env and differ only in path, seed and control iterate, so here every
+    iteration is ONE `pg_rollout_multi` launch over all Q*M rollouts, Q segment-wise exp-weighted updates and one replay
+    launch of the Q updated iterates.  Problem q reproduces a single StochTrajOptimizer with seed `seeds[q]` exactly
+    (same generator stream, same update kernel).
+    """
+
+    def __init__(self, env, paths, seeds, sigma=0.2, kappa=5, alpha=1, Num_processes=64, Traj_per_process=15, TimeSteps=200,
+                 Iterations=20, verbose=0, **kwargs):
+        assert len(paths) == len(seeds)
+        self.env, self.paths, self.seeds = env, [list(p) for p in paths], list(seeds)
+        self.sigma, self.kappa, self.alpha = sigma, kappa, alpha
+        self.M = Num_processes * Traj_per_process
+        self.N, self.ITER, self.verbose, self.kwargs = TimeSteps, Iterations, verbose, kwargs
+
+    def optimize(self):
+        Q, M, N = len(self.paths), self.M, self.N
+        world = self.env(render=False, device="cuda", **self.kwargs)
+        eng, D = world.engine, world.action_space.shape[0]
+        dev = eng._dev()
+        gens = []
+        for s in self.seeds:
+            g = torch.Generator(device=dev)
+            g.manual_seed(s)
+            gens.append(g)
+        paths = np.asarray([p[:N] for p in self.paths], np.int32)
+        prob = torch.arange(Q, dtype=torch.int32, device=dev).repeat_interleave(M).contiguous()
+        prob1 = torch.arange(Q, dtype=torch.int32, device=dev).contiguous()
+        u = torch.zeros((Q, N, D), dtype=torch.float64, device=dev)
+        uopt = u.clone()
+        Jopt = np.full(Q, np.inf)
+        logs = [[] for _ in range(Q)]
+        zero_noise = torch.zeros((Q, N, D), dtype=torch.float32, device=dev)
+        for it in range(self.ITER):
+            noise = torch.cat([torch.randn((M, N, D), generator=g, device=dev, dtype=torch.float32) * float(self.sigma) for g in gens])
+            J = eng.rollout_multi(u, noise, prob, paths, world.max_forces)
+            for q in range(Q):
+                EN.mppi_update(J[q * M:(q + 1) * M], noise[q * M:(q + 1) * M], u[q], self.kappa, self.alpha, apply=True)
+            Jcur = eng.rollout_multi(u, zero_noise, prob1, paths, world.max_forces).cpu().numpy()      # replay_traj of every problem
+            for q in range(Q):
+                if Jcur[q] <= Jopt[q]:
+                    Jopt[q] = Jcur[q]
+                    uopt[q] = u[q]
+                logs[q].append(-Jopt[q])
+            if self.verbose:
+                print(f"Iter {it + 1}: best R per problem {np.round(-Jopt, 2).tolist()}")
+        return uopt.cpu().numpy(), -Jopt, logs

@@ -301,3 +301,39 @@ def test_csg_node_scores_match_oracle(EN):
         assert abs(got[n] - ref) <= 2e-5 * max(1.0, abs(ref)), (n, got[n], ref)
     table, ids, _, _ = G.select_paths(nodes[:10], got[:10], nodes, got)
     assert ids.shape == (10, 2) and table.shape[1] == 2
+
+
+def test_multi_problem_rollouts_equal_separate_problems(EN):
+    """pg_rollout_multi: Q problems (own controls, own path) in one launch == Q single-problem launches, bit for bit; the
+    multi-problem optimiser reproduces StochTrajOptimizer per problem (model_optimize.py:74-117 runs them serially)."""
+    from synthesize_pregrasp_b200.envs import envs_dict
+    from synthesize_pregrasp_b200.envspec import make_spec
+    from synthesize_pregrasp_b200.stoch_traj_opt import MultiStochTrajOptimizer, StochTrajOptimizer
+    spec = make_spec("plate")
+    eng = EN.RolloutEngine(spec, device=0)
+    gen = torch.Generator(device="cuda:0").manual_seed(9)
+    Q, M, N = 3, 40, 2
+    u = 0.3 * torch.randn((Q, N, 48), generator=gen, device="cuda:0", dtype=torch.float64)
+    noise = 0.8 * torch.randn((Q * M, N, 48), generator=gen, device="cuda:0", dtype=torch.float32)
+    n_states = len(spec.dummy_states)
+    paths = np.array([[q % n_states, (q + 1) % n_states] for q in range(Q)], np.int32)
+    prob = torch.arange(Q, dtype=torch.int32, device="cuda:0").repeat_interleave(M).contiguous()
+    J, metric = eng.rollout_multi(u, noise, prob, paths, 20.0, want_metric=True)
+    for q in range(Q):
+        Jq, mq = eng.rollout(u[q], noise[q * M:(q + 1) * M].contiguous(), paths[q], 20.0, want_metric=True)
+        assert torch.equal(J[q * M:(q + 1) * M], Jq) and torch.equal(metric[q * M:(q + 1) * M], mq), q
+    # interleaved problem indices: same rollouts, permuted
+    perm = torch.randperm(Q * M, generator=torch.Generator().manual_seed(1)).to("cuda:0")
+    J2 = eng.rollout_multi(u, noise[perm].contiguous(), prob[perm].contiguous(), paths, 20.0)
+    assert torch.equal(J2, J[perm])
+    kw = dict(sigma=0.8, TimeSteps=2, Iterations=2, active_finger_tips=[0, 1], num_interp_f=7, Num_processes=4, Traj_per_process=10,
+              opt_time=False, mode="only_score", steps=2, has_distance_field=True, max_forces=20.0, validate=False)
+    seeds = [11, 12]
+    multi = MultiStochTrajOptimizer(envs_dict["foodbox"], paths=[[0, 0, 0], [0, 0, 0]], seeds=seeds, path=np.array([0, 0, 0]), **kw)
+    uopt, ropt, logs = multi.optimize()
+    for q, sd in enumerate(seeds):
+        single = StochTrajOptimizer(env=envs_dict["foodbox"], seed=sd, render=False, initial_guess=None, verbose=0,
+                                    path=np.array([0, 0, 0]), **kw)
+        u1, r1, log1, _ = single.optimize()
+        np.testing.assert_allclose(uopt[q], u1, rtol=0, atol=1e-12)
+        assert abs(ropt[q] - r1) <= 1e-9 * max(1.0, abs(r1))
