@@ -25,6 +25,9 @@ WORKLOADS = {   # BASELINE.json configs: env, max force, K per GPU
     "plate_K65536": dict(env="plate", force=20.0, K=65536),        # configs[0]'s task at the headline batch size
     "plate_K360": dict(env="plate", force=20.0, K=360),            # configs[0] as the reference runs it: 12 workers x 30 (model_optimize.py:77)
     "waterbottle_K65536": dict(env="waterbottle", force=20.0, K=65536),   # SURVEY 8(d) config 4, per-GPU share
+    # the reference's whole plate job per MPPI iteration: 10 contact-state paths x 3 runs (model_optimize.py:74-117), each with
+    # its 12 x 30 samples, as ONE multi-problem launch (pg_rollout_multi) instead of 30 serial optimisers
+    "plate_Q30xK360": dict(env="plate", force=20.0, K=30 * 360, Q=30),
 }
 SIGMA, KAPPA, ALPHA, N_STEPS, D = 0.8, 5.0, 1.0, 2, 48
 
@@ -174,7 +177,19 @@ def main():
     path = [0, 0]
     L = _abi.lib()
 
+    Q = wl.get("Q", 0)
+    if Q:
+        uQ = torch.zeros((Q, N_STEPS, D), dtype=torch.float64, device=dev)
+        probQ = torch.arange(Q, dtype=torch.int32, device=dev).repeat_interleave(K // Q).contiguous()
+        pathsQ = np.zeros((Q, N_STEPS), np.int32)
+
     def step_device():
+        if Q:
+            J = eng.rollout_multi(uQ, noise, probQ, pathsQ, wl["force"])
+            M = K // Q
+            for q in range(Q):
+                part = EN.mppi_update(J[q * M:(q + 1) * M], noise[q * M:(q + 1) * M], None, KAPPA, ALPHA, apply=False, want_partial=True)
+            return J
         J = eng.rollout(u, noise, path, wl["force"])
         part = EN.mppi_update(J, noise, None, KAPPA, ALPHA, apply=False, want_partial=True)
         if world > 1:
