@@ -14,8 +14,13 @@
 
 namespace pg {
 
+#ifndef TC_THREADS
 #define TC_THREADS 256
+#endif
 #define TC_M 128
+#define TC_NS (TC_THREADS / TC_M)          // column groups: each thread owns one point row and 1/TC_NS of the channels
+#define TC_CH (C2 / TC_NS)                // conv2 channels per thread
+#define TC_COLS (C3 / TC_NS)              // accumulator columns per thread
 
 
 struct TcSmem {
@@ -83,9 +88,9 @@ __device__ __forceinline__ float tc_box_dist(double x, double y, double z, const
   return (float)(outside > 0 ? outside : fmax(inside, 0.0));
 }
 
-// conv1 + 32 of the 64 conv2 channels (HALF selects which) for point p; weights broadcast from shared memory
-template <int HALF>
-__device__ __forceinline__ void point_h2_half_t(const TcSmem& s, const CostDev& cd, int p, float df, float* out) {
+// conv1 + TC_CH of the 64 conv2 channels (group G selects which) for point p; weights broadcast from shared memory
+template <int G>
+__device__ __forceinline__ void point_h2_grp_t(const TcSmem& s, const CostDev& cd, int p, float df, float* out) {
   float h1[C1];
   const float4* a = reinterpret_cast<const float4*>(cd.a1 + (size_t)p * C1);
 #pragma unroll
@@ -97,20 +102,29 @@ __device__ __forceinline__ void point_h2_half_t(const TcSmem& s, const CostDev& 
     h1[4 * j + 3] = fmaxf(fmaf(s.w1d[4 * j + 3], df, v.w), 0.f);
   }
 #pragma unroll
-  for (int c = 0; c < 32; c++) out[c] = s.b2[HALF * 32 + c];
+  for (int c = 0; c < TC_CH; c++) out[c] = s.b2[G * TC_CH + c];
 #pragma unroll
   for (int j = 0; j < C1; j++) {
-    const float4* w = reinterpret_cast<const float4*>(s.w2t + j * C2 + HALF * 32);
+    const float4* w = reinterpret_cast<const float4*>(s.w2t + j * C2 + G * TC_CH);
 #pragma unroll
-    for (int c4 = 0; c4 < 8; c4++) {
+    for (int c4 = 0; c4 < TC_CH / 4; c4++) {
       float4 wv = w[c4];
       out[4 * c4] = fmaf(wv.x, h1[j], out[4 * c4]); out[4 * c4 + 1] = fmaf(wv.y, h1[j], out[4 * c4 + 1]);
       out[4 * c4 + 2] = fmaf(wv.z, h1[j], out[4 * c4 + 2]); out[4 * c4 + 3] = fmaf(wv.w, h1[j], out[4 * c4 + 3]);
     }
   }
 }
-__device__ __forceinline__ void point_h2_half(const TcSmem& s, const CostDev& cd, int p, float df, int half, float* out) {
-  if (half == 0) point_h2_half_t<0>(s, cd, p, df, out); else point_h2_half_t<1>(s, cd, p, df, out);   // warp-uniform
+__device__ __forceinline__ void point_h2_grp(const TcSmem& s, const CostDev& cd, int p, float df, int grp, float* out) {   // grp is warp-uniform
+  switch (grp) {
+    case 0: point_h2_grp_t<0>(s, cd, p, df, out); break;
+    case 1: point_h2_grp_t<1>(s, cd, p, df, out); break;
+#if TC_NS > 2
+    case 2: point_h2_grp_t<2>(s, cd, p, df, out); break;
+    default: point_h2_grp_t<3>(s, cd, p, df, out); break;
+#else
+    default: break;
+#endif
+  }
 }
 // +c, ReLU and the conv4 partial sums of 32 accumulator columns [cbase, cbase+32)
 __device__ __forceinline__ void conv4_block(const TcSmem& s, int cbase, const uint32_t* v, float* out) {
@@ -133,7 +147,7 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid & (TC_M - 1), half = tid >> 7;       // TMEM lane / point row of this thread, column half
+  const int row = tid & (TC_M - 1), grp = tid >> 7;        // TMEM lane / point row of this thread, column group
   const int P = cd.n_cloud;
 
   // ---- one-time setup: weights into shared memory (W3a in the canonical layout), TMEM allocation, mbarrier
@@ -232,20 +246,20 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
       __syncthreads();
     }
     // ---------------- stage 1: g = masked max over points of conv2 (this thread: 32 channels of its rows)
-    float gmax[32];
+    float gmax[TC_CH];
 #pragma unroll
-    for (int c = 0; c < 32; c++) gmax[c] = -INFINITY;
+    for (int c = 0; c < TC_CH; c++) gmax[c] = -INFINITY;
     for (int t0 = 0; t0 < P; t0 += TC_M) {
       int p = t0 + row;
       if (p < P && s.msk[p]) {
-        float h2[32];
-        point_h2_half(s, cd, p, s.df[p], half, h2);
+        float h2[TC_CH];
+        point_h2_grp(s, cd, p, s.df[p], grp, h2);
 #pragma unroll
-        for (int c = 0; c < 32; c++) gmax[c] = fmaxf(gmax[c], h2[c]);
+        for (int c = 0; c < TC_CH; c++) gmax[c] = fmaxf(gmax[c], h2[c]);
       }
     }
 #pragma unroll
-    for (int c = 0; c < 32; c++) {
+    for (int c = 0; c < TC_CH; c++) {
       float v = gmax[c];
       for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
       gmax[c] = v;
@@ -253,19 +267,19 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     __syncthreads();
     if (lane == 0) {
-      for (int c = 0; c < 32; c++) s.red[warp * 32 + c] = gmax[c];     // warps 0-3: channels 0-31, warps 4-7: 32-63
+      for (int c = 0; c < TC_CH; c++) s.red[warp * TC_CH + c] = gmax[c];     // the four warps of group g hold channels g*TC_CH ..
       reinterpret_cast<int*>(s.red + 8 * 32)[warp] = cnt;
     }
     __syncthreads();
     if (tid < C2) {
-      int h = tid >> 5, c = tid & 31;
-      float v = s.red[(4 * h) * 32 + c];
-      for (int w = 1; w < 4; w++) v = fmaxf(v, s.red[(4 * h + w) * 32 + c]);
+      int h = tid / TC_CH, c = tid % TC_CH;
+      float v = s.red[(4 * h) * TC_CH + c];
+      for (int w = 1; w < 4; w++) v = fmaxf(v, s.red[(4 * h + w) * TC_CH + c]);
       s.g[tid] = v;
     }
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < 8; w++) t += reinterpret_cast<int*>(s.red + 8 * 32)[w];
+      for (int w = 0; w < TC_THREADS / 32; w++) t += reinterpret_cast<int*>(s.red + 8 * 32)[w];
       s.count = t;
     }
     __syncthreads();
@@ -274,7 +288,7 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
       __syncthreads();
       continue;
     }
-    {
+    if (tid < C3) {
       float v = cd.b3[tid];
       for (int k = 0; k < C2; k++) v = fmaf(__ldg(cd.w3bt + k * C3 + tid), s.g[k], v);
       s.c[tid] = v;
@@ -288,20 +302,20 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
     for (int t0 = 0; t0 < P; t0 += TC_M) {
       const int p = t0 + row;
       {
-        float h2[32];
-        if (p < P) point_h2_half(s, cd, p, s.df[p], half, h2);
+        float h2[TC_CH];
+        if (p < P) point_h2_grp(s, cd, p, s.df[p], grp, h2);
         else {
 #pragma unroll
-          for (int c = 0; c < 32; c++) h2[c] = 0.f;
+          for (int c = 0; c < TC_CH; c++) h2[c] = 0.f;
         }
         // split a = hi + lo; hi goes to the operand buffer now, lo is kept in registers for the second phase
-        float lo[32];
+        float lo[TC_CH];
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
+        for (int q = 0; q < TC_CH / 4; q++) {
           float4 hi;
           hi.x = tf32_rna(h2[4 * q]); hi.y = tf32_rna(h2[4 * q + 1]); hi.z = tf32_rna(h2[4 * q + 2]); hi.w = tf32_rna(h2[4 * q + 3]);
           lo[4 * q] = h2[4 * q] - hi.x; lo[4 * q + 1] = h2[4 * q + 1] - hi.y; lo[4 * q + 2] = h2[4 * q + 2] - hi.z; lo[4 * q + 3] = h2[4 * q + 3] - hi.w;
-          *reinterpret_cast<float4*>(s.a_buf + ((half * 8 + q) * TC_M + row) * 4) = hi;
+          *reinterpret_cast<float4*>(s.a_buf + ((grp * (TC_CH / 4) + q) * TC_M + row) * 4) = hi;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;");
@@ -321,8 +335,8 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
         phase ^= 1;
         // second phase: the same buffer now carries a_lo
 #pragma unroll
-        for (int q = 0; q < 8; q++)
-          *reinterpret_cast<float4*>(s.a_buf + ((half * 8 + q) * TC_M + row) * 4) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+        for (int q = 0; q < TC_CH / 4; q++)
+          *reinterpret_cast<float4*>(s.a_buf + ((grp * (TC_CH / 4) + q) * TC_M + row) * 4) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();
@@ -337,14 +351,14 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;");
       }
-      // epilogue: this thread owns accumulator row `row`, columns half*128 .. +128
+      // epilogue: this thread owns accumulator row `row`, columns grp*TC_COLS .. +TC_COLS
       float out[C4];
 #pragma unroll
       for (int o = 0; o < C4; o++) out[o] = 0.f;
 #pragma unroll
-      for (int cb = 0; cb < 4; cb++) {
+      for (int cb = 0; cb < TC_COLS / 32; cb++) {
         uint32_t v[32];
-        uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 128 + cb * 32);
+        uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * TC_COLS + cb * 32);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -355,20 +369,25 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        conv4_block(s, half * 128 + cb * 32, v, out);
+        conv4_block(s, grp * TC_COLS + cb * 32, v, out);
       }
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncthreads();                                             // all TMEM reads done; A buffers free
-      float* xch = s.a_buf;                                        // exchange the upper-half partial sums
-      if (half == 1) {
+      float* xch = s.a_buf;                                        // exchange the partial sums of groups 1..TC_NS-1
+      if (grp > 0) {
 #pragma unroll
-        for (int o = 0; o < C4; o++) xch[o * TC_M + row] = out[o];
+        for (int o = 0; o < C4; o++) xch[((grp - 1) * C4 + o) * TC_M + row] = out[o];
       }
       __syncthreads();
-      if (half == 0) {
+      if (grp == 0) {
         float m = (p < P && s.msk[p]) ? 0.f : -INFINITY;
 #pragma unroll
-        for (int o = 0; o < C4; o++) rmax[o] = fmaxf(rmax[o], out[o] + xch[o * TC_M + row] + s.b4[o] + m);
+        for (int o = 0; o < C4; o++) {
+          float acc = out[o];
+#pragma unroll
+          for (int gg = 0; gg < TC_NS - 1; gg++) acc += xch[(gg * C4 + o) * TC_M + row];
+          rmax[o] = fmaxf(rmax[o], acc + s.b4[o] + m);
+        }
       }
       __syncthreads();
     }
@@ -379,7 +398,7 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
       for (int k = 16; k > 0; k >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, k));
       rmax[o] = v;
     }
-    if (half == 0 && lane == 0) for (int o = 0; o < C4; o++) s.red[warp * C4 + o] = rmax[o];
+    if (grp == 0 && lane == 0) for (int o = 0; o < C4; o++) s.red[warp * C4 + o] = rmax[o];
     __syncthreads();
     if (tid < C4) {
       float v = s.red[tid];
