@@ -44,6 +44,14 @@ struct TcSmem {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// two independent fp32 FMAs in one instruction (FFMA2): d = a * b + d, bit-identical to two fmaf
+__device__ __forceinline__ void ffma2(float2& d, float2 a, float2 b) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a), bb = *reinterpret_cast<const unsigned long long*>(&b);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -107,10 +115,12 @@ __device__ __forceinline__ void point_h2_grp_t(const TcSmem& s, const CostDev& c
   for (int j = 0; j < C1; j++) {
     const float4* w = reinterpret_cast<const float4*>(s.w2t + j * C2 + G * TC_CH);
 #pragma unroll
+    const float2 hh = make_float2(h1[j], h1[j]);
     for (int c4 = 0; c4 < TC_CH / 4; c4++) {
       float4 wv = w[c4];
-      out[4 * c4] = fmaf(wv.x, h1[j], out[4 * c4]); out[4 * c4 + 1] = fmaf(wv.y, h1[j], out[4 * c4 + 1]);
-      out[4 * c4 + 2] = fmaf(wv.z, h1[j], out[4 * c4 + 2]); out[4 * c4 + 3] = fmaf(wv.w, h1[j], out[4 * c4 + 3]);
+      float2* o2 = reinterpret_cast<float2*>(out + 4 * c4);
+      ffma2(o2[0], make_float2(wv.x, wv.y), hh);
+      ffma2(o2[1], make_float2(wv.z, wv.w), hh);
     }
   }
 }
@@ -133,10 +143,12 @@ __device__ __forceinline__ void conv4_block(const TcSmem& s, int cbase, const ui
     float h = fmaxf(__uint_as_float(v[j]) + s.c[cbase + j], 0.f);
     const float4* w = reinterpret_cast<const float4*>(s.w4t + (cbase + j) * C4);
 #pragma unroll
+    const float2 hh = make_float2(h, h);
     for (int o4 = 0; o4 < C4 / 4; o4++) {
       float4 wv = w[o4];
-      out[4 * o4] = fmaf(wv.x, h, out[4 * o4]); out[4 * o4 + 1] = fmaf(wv.y, h, out[4 * o4 + 1]);
-      out[4 * o4 + 2] = fmaf(wv.z, h, out[4 * o4 + 2]); out[4 * o4 + 3] = fmaf(wv.w, h, out[4 * o4 + 3]);
+      float2* o2 = reinterpret_cast<float2*>(out + 4 * o4);
+      ffma2(o2[0], make_float2(wv.x, wv.y), hh);
+      ffma2(o2[1], make_float2(wv.z, wv.w), hh);
     }
   }
 }
