@@ -138,6 +138,18 @@ int pg_dyn_sweep_simple(const double* cloud_pts_dev, const double* cloud_nrm_dev
                         uint64_t first, uint64_t last, int32_t* triples_out_dev, uint64_t cap,
                         unsigned long long* count_dev, void* stream);
 
+/* utils/dyn_feasibility_check.py:28-112 check_dyn_feasible: the wrench-closure QP (min 1/2 |net wrench|^2 over friction pyramids
+ * mu, normal forces >= f_min; reference values mu = 5, f_min = MIN_NORMAL_FORCE[3] = 1) solved exactly per contact triple; a grasp
+ * is feasible when some triple reaches objective <= tol (2e-3 at :77, 1e-4 in the sweep).  obj_out_dev [B] (nullable): smallest
+ * objective seen.  The reference solves the same QP with cvxpy/OSQP to solver tolerance: decisions can differ for objectives
+ * within that tolerance of tol (parity unpinned). */
+int pg_dyn_feasible_qp(const double* pts_dev, const double* nrm_dev, const int32_t* count_dev, int B, int M, double mu, double f_min,
+                       double tol, uint8_t* out_dev, double* obj_out_dev, void* stream);
+/* find_dynamically_feasible_contacts :239-303 as written (QP criterion, min-distance prefilter), triple range [first,last) */
+int pg_dyn_sweep_qp(const double* cloud_pts_dev, const double* cloud_nrm_dev, int P, double min_dist, double mu, double f_min,
+                    double tol, uint64_t first, uint64_t last, int32_t* triples_out_dev, uint64_t cap,
+                    unsigned long long* count_dev, void* stream);
+
 /* diagnostics: number of kernel launches issued through this library since load */
 uint64_t pg_launch_count(void);
 

@@ -4,8 +4,10 @@ simple_check_*: restates utils/dyn_feasibility_check.py:124-235 (project2norm, c
 `c1<0 and c1<0` typo, check_sign_change, simple_check_dyn_feasible_3p, simple_check_dyn_feasible); the two
 pytorch_kinematics calls at :191-196 (axis_angle_to_quaternion, quaternion_apply) are restated from their
 published definitions (pytorch3d transforms) in float64.
-qp_matrices: the QP data of :28-60 / :93-101 (Q, G, h and the 6x9 wrench map).  The QP SOLVE is not restated: its
-optimum is PARITY UNPINNED (cvxpy/OSQP absent, nothing recorded) and no kernel is shipped for it this round.
+qp_matrices: the QP data of :28-60 / :93-101 (Q, G, h and the 6x9 wrench map).  qp_objective / check_dyn_feasible_qp solve that
+QP -- the reference's own (Q, G, h) formulation -- with scipy's SLSQP instead of cvxpy/OSQP.  PARITY UNPINNED: nothing in the
+reference records a QP optimum and its solver cannot be installed, so this pins the kernel to an independent exact solve of the
+same problem, not to the reference's solver output (which is only accurate to OSQP's tolerance anyway).
 """
 import itertools
 
@@ -130,3 +132,29 @@ def qp_matrices(p, nrm_unit_or_raw, mu=MU, normalise=True):
     h = np.hstack([np.zeros(12), -np.ones(3)]) * MIN_NORMAL_FORCE_3
     W = np.hstack([A1, A2]).T                                   # 6x9 wrench map, Q = W^T W
     return Q, G, h, W
+
+
+def qp_objective(p, nrm, normalise=True, mu=MU):
+    """Optimal value of construct_and_solve_wrench_closure_qp (:62-75) for one triple, by SLSQP on (Q, G, h)."""
+    from scipy.optimize import minimize
+    Q, G, h, _ = qp_matrices(np.asarray(p, float), np.asarray(nrm, float), mu, normalise)
+    z0 = np.tile([-2.0 * MIN_NORMAL_FORCE_3, 0.0, 0.0], 3)
+    r = minimize(lambda z: 0.5 * z @ Q @ z, z0, jac=lambda z: Q @ z, method="SLSQP", options={"ftol": 1e-15, "maxiter": 1000},
+                 constraints=[{"type": "ineq", "fun": lambda z: h - G @ z, "jac": lambda z: -G}])
+    return float(r.fun)
+
+
+def check_dyn_feasible_qp(points, normals, tol=2e-3):
+    """check_dyn_feasible (:77-112): first triple of the present contacts (x < 50) whose QP optimum is <= tol.
+    -> (decision, smallest objective met before deciding)."""
+    import itertools
+    points, normals = np.asarray(points, float), np.asarray(normals, float)
+    keep = points[:, 0] < 50
+    points, normals = points[keep], normals[keep]
+    best = np.inf
+    for comb in itertools.combinations(range(len(points)), 3):
+        o = qp_objective(points[list(comb)], normals[list(comb)], normalise=True)
+        best = min(best, o)
+        if o <= tol:
+            return True, best
+    return False, best

@@ -175,8 +175,11 @@ def lib():
     L.pg_mppi_merge_apply.argtypes = [_DP, i32, i32, i32, f64, f64, _DP]
     L.pg_dyn_feasible_simple.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     L.pg_dyn_sweep_simple.argtypes = [vp, vp, i32, f64, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp]
+    L.pg_dyn_feasible_qp.argtypes = [vp, vp, vp, i32, i32, f64, f64, f64, vp, vp, vp]
+    L.pg_dyn_sweep_qp.argtypes = [vp, vp, i32, f64, f64, f64, f64, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp]
     for f in ("pg_env_create", "pg_env_destroy", "pg_rollout", "pg_rollout_multi", "pg_rollout_host", "pg_physics", "pg_cost", "pg_score",
-              "pg_mppi_update", "pg_mppi_merge_apply", "pg_dyn_feasible_simple", "pg_dyn_sweep_simple"):
+              "pg_mppi_update", "pg_mppi_merge_apply", "pg_dyn_feasible_simple", "pg_dyn_sweep_simple", "pg_dyn_feasible_qp",
+              "pg_dyn_sweep_qp"):
         getattr(L, f).restype = C.c_int
     _lib = L
     return L
@@ -184,6 +187,7 @@ def lib():
 
 EXPORTS = ("pg_last_error", "pg_version", "pg_env_create", "pg_env_destroy", "pg_rollout", "pg_rollout_multi", "pg_rollout_host", "pg_physics",
            "pg_cost", "pg_score", "pg_mppi_update", "pg_mppi_merge_apply", "pg_dyn_feasible_simple", "pg_dyn_sweep_simple",
+           "pg_dyn_feasible_qp", "pg_dyn_sweep_qp",
            "pg_launch_count")
 
 

@@ -3,6 +3,7 @@
 // find_dynamically_feasible_contacts :239-303 with the :260-265 pairwise-distance prefilter, enumerating the
 // triple index space on the fly (no materialised triples in HBM) with on-device compaction.
 #include "pg_internal.h"
+#include "pg_qp.cuh"
 
 namespace pg {
 
@@ -157,6 +158,50 @@ __global__ void dyn_sweep_kernel(const double* __restrict__ pts, const double* _
   }
 }
 
+// ---- wrench-closure QP criterion (check_dyn_feasible :77-112 and the sweep :239-303 as written, with the QP) -------------
+__device__ __forceinline__ V3 ld3(const double* p, int i) { return V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+
+// one thread per grasp of M contacts: first triple (itertools.combinations order) whose objective is <= tol decides;
+// normals are normalised per contact as :94 does.  obj_out (nullable) [B]: the smallest objective met before the decision.
+__global__ void dyn_qp_kernel(const double* __restrict__ pts, const double* __restrict__ nrm, const int* __restrict__ count,
+                              int B, int M, double mu, double f_min, double tol, uint8_t* __restrict__ out, double* __restrict__ obj_out) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int m = count ? count[b] : M;
+  const double* p = pts + (size_t)b * M * 3;
+  const double* n = nrm + (size_t)b * M * 3;
+  bool res = false;
+  double best = INFINITY;
+  for (int i = 0; i < m && !res; i++)
+    for (int j = i + 1; j < m && !res; j++)
+      for (int k = j + 1; k < m && !res; k++) {
+        V3 P[3] = {ld3(p, i), ld3(p, j), ld3(p, k)}, Nn[3] = {ld3(n, i), ld3(n, j), ld3(n, k)};
+        for (int q = 0; q < 3; q++) Nn[q] = Nn[q] / len(Nn[q]);
+        double o = qp::wrench_closure_objective(P, Nn, mu, f_min, nullptr);
+        if (o < best) best = o;
+        res = o <= tol;
+      }
+  out[b] = res ? 1 : 0;
+  if (obj_out) obj_out[b] = best;
+}
+
+__global__ void dyn_sweep_qp_kernel(const double* __restrict__ pts, const double* __restrict__ nrm, int P, double min_dist,
+                                    double mu, double f_min, double tol, unsigned long long first, unsigned long long last,
+                                    int* __restrict__ triples, unsigned long long cap, unsigned long long* __restrict__ count) {
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long r = first + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; r < last; r += stride) {
+    int i, j, k;
+    unrank3(r, P, i, j, k);
+    V3 Pp[3] = {ld3(pts, i), ld3(pts, j), ld3(pts, k)};
+    if (len(Pp[0] - Pp[1]) < min_dist || len(Pp[0] - Pp[2]) < min_dist || len(Pp[1] - Pp[2]) < min_dist) continue;   // :259-265
+    V3 Nn[3] = {ld3(nrm, i), ld3(nrm, j), ld3(nrm, k)};                                   // cloud normals used as given (:271)
+    if (qp::wrench_closure_objective(Pp, Nn, mu, f_min, nullptr) <= tol) {
+      unsigned long long slot = atomicAdd(count, 1ull);
+      if (triples && slot < cap) { triples[3 * slot] = i; triples[3 * slot + 1] = j; triples[3 * slot + 2] = k; }
+    }
+  }
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -185,6 +230,35 @@ extern "C" int pg_dyn_sweep_simple(const double* cloud_pts_dev, const double* cl
   int blocks = (int)((n + 127) / 128 < (uint64_t)sms * 16 ? (n + 127) / 128 : (uint64_t)sms * 16);
   dyn_sweep_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(cloud_pts_dev, cloud_nrm_dev, P, min_dist, first, last,
                                                             triples_out_dev, cap, count_dev);
+  count_launch();
+  PG_CUDA(cudaGetLastError());
+  return PG_OK;
+}
+
+extern "C" int pg_dyn_feasible_qp(const double* pts_dev, const double* nrm_dev, const int32_t* count_dev, int B, int M, double mu,
+                                  double f_min, double tol, uint8_t* out_dev, double* obj_out_dev, void* stream) {
+  if (!pts_dev || !nrm_dev || !out_dev || B < 0 || M < 3 || M > 8 || !(mu > 0) || !(f_min > 0)) { set_error("pg_dyn_feasible_qp: bad arguments"); return PG_ERR_INVALID; }
+  if (B == 0) return PG_OK;
+  dyn_qp_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(pts_dev, nrm_dev, count_dev, B, M, mu, f_min, tol, out_dev, obj_out_dev);
+  count_launch();
+  PG_CUDA(cudaGetLastError());
+  return PG_OK;
+}
+
+extern "C" int pg_dyn_sweep_qp(const double* cloud_pts_dev, const double* cloud_nrm_dev, int P, double min_dist, double mu, double f_min,
+                               double tol, uint64_t first, uint64_t last, int32_t* triples_out_dev, uint64_t cap,
+                               unsigned long long* count_dev, void* stream) {
+  if (!cloud_pts_dev || !cloud_nrm_dev || !count_dev || P < 3 || !(mu > 0) || !(f_min > 0)) { set_error("pg_dyn_sweep_qp: bad arguments"); return PG_ERR_INVALID; }
+  uint64_t total = (uint64_t)P * (P - 1) * (P - 2) / 6;
+  if (last > total) last = total;
+  if (first >= last) return PG_OK;
+  int dev = 0, sms = 148;
+  PG_CUDA(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  uint64_t n = last - first;
+  int blocks = (int)((n + 63) / 64 < (uint64_t)sms * 16 ? (n + 63) / 64 : (uint64_t)sms * 16);
+  dyn_sweep_qp_kernel<<<blocks, 64, 0, (cudaStream_t)stream>>>(cloud_pts_dev, cloud_nrm_dev, P, min_dist, mu, f_min, tol, first, last,
+                                                              triples_out_dev, cap, count_dev);
   count_launch();
   PG_CUDA(cudaGetLastError());
   return PG_OK;

@@ -3,6 +3,7 @@
 // GPU time is spent.  Not part of the product, not a fallback: the shipped library has no CPU path.
 #include "../../synthesize_pregrasp_b200/csrc/pg_envbuild.h"
 #include "../../synthesize_pregrasp_b200/csrc/pg_rollout.cuh"
+#include "../../synthesize_pregrasp_b200/csrc/pg_qp.cuh"
 
 #ifdef PG_HOST_STATS
 namespace pg { long g_stat_pts[32], g_stat_nc[16]; }
@@ -30,4 +31,22 @@ extern "C" int hostsim_rollout(const PgEnvSpec* sp, const double* u, const float
     else pg::rollout_one<pg::SHAPE_BOX>(E, u, noise ? noise + (size_t)k * N * 48 : nullptr, N, path, max_force, train, out, sm, 1);
   }
   return 0;
+}
+
+// wrench-closure QP objective of one contact triple (csrc/pg_qp.cuh), host build
+extern "C" double hostsim_qp(const double* p9, const double* n9, double mu, double f_min, int* iters) {
+  pg::V3 p[3], n[3];
+  for (int i = 0; i < 3; i++) { p[i] = pg::V3(p9[3 * i], p9[3 * i + 1], p9[3 * i + 2]); n[i] = pg::V3(n9[3 * i], n9[3 * i + 1], n9[3 * i + 2]); }
+  return pg::qp::wrench_closure_objective(p, n, mu, f_min, iters);
+}
+
+extern "C" int hostsim_nnls(const double* A, const double* y, double* x) {
+  double M[pg::qp::ROWS][pg::qp::COLS];
+  for (int r = 0; r < pg::qp::ROWS; r++) for (int c = 0; c < pg::qp::COLS; c++) M[r][c] = A[r * pg::qp::COLS + c];
+  return pg::qp::nnls(M, y, x);
+}
+extern "C" void hostsim_ls(const double* A, const double* y, const int* idx, int np, double* s) {
+  double M[pg::qp::ROWS][pg::qp::COLS];
+  for (int r = 0; r < pg::qp::ROWS; r++) for (int c = 0; c < pg::qp::COLS; c++) M[r][c] = A[r * pg::qp::COLS + c];
+  pg::qp::ls_passive(M, y, idx, np, s);
 }

@@ -337,3 +337,50 @@ def test_multi_problem_rollouts_equal_separate_problems(EN):
         u1, r1, log1, _ = single.optimize()
         np.testing.assert_allclose(uopt[q], u1, rtol=0, atol=1e-12)
         assert abs(ropt[q] - r1) <= 1e-9 * max(1.0, abs(r1))
+
+
+def test_dyn_feasibility_qp_kernels(EN):
+    """pg_dyn_feasible_qp / pg_dyn_sweep_qp vs the oracle's independent solve of the reference QP (parity unpinned vs cvxpy)."""
+    from oracle import dynfeas as DF
+    from synthesize_pregrasp_b200 import dyn_feasibility_check as DYN
+    rng = np.random.RandomState(21)
+    B, M = 60, 4
+    pts = rng.uniform(-0.2, 0.2, (B, M, 3))
+    nrm = rng.randn(B, M, 3)
+    nrm[::2] = pts[::2] - pts[::2].mean(1, keepdims=True)        # closure-like half
+    pts[5, 3, 0] = 100.0                                          # an absent finger (x >= 50)
+    dec, obj = DYN.check_dyn_feasible(pts, nrm, tol=2e-3, return_objective=True)
+    n_close = 0
+    for b in range(B):
+        rd, ro = DF.check_dyn_feasible_qp(pts[b], nrm[b], tol=2e-3)
+        if abs(ro - 2e-3) <= 1e-5:                                # within solver noise of the threshold: either decision is defensible
+            n_close += 1
+            continue
+        assert bool(dec[b]) == rd, (b, obj[b], ro)
+        assert abs(obj[b] - ro) <= 1e-6 * max(1.0, ro) + 1e-8, (b, obj[b], ro)
+    assert n_close <= 3 and 5 < dec.sum() < B
+    one = DYN.check_dyn_feasible(pts[0], nrm[0], tol=2e-3)
+    assert one == bool(dec[0])
+    # sweep with the QP criterion == brute force over all triples of a small cloud, also when split in two ranges
+    P = 14
+    cp = rng.uniform(-0.15, 0.15, (P, 3))
+    cn = cp - cp.mean(0) + 0.05 * rng.randn(P, 3)
+    cn /= np.linalg.norm(cn, axis=1)[:, None]
+    tri, n = DYN.find_dynamically_feasible_contacts(cp, cn, criterion="qp", tol=1e-4)
+    import itertools
+    want = set()
+    for c in itertools.combinations(range(P), 3):
+        q = cp[list(c)]
+        if min(np.linalg.norm(q[0] - q[1]), np.linalg.norm(q[0] - q[2]), np.linalg.norm(q[1] - q[2])) < 0.03:
+            continue
+        o = DF.qp_objective(q, cn[list(c)], normalise=False)
+        if abs(o - 1e-4) <= 1e-6:
+            continue
+        if o <= 1e-4:
+            want.add(c)
+    got = {tuple(t) for t in tri.tolist()}
+    assert want <= got and len(got - want) <= 2, (len(want), len(got))
+    total = P * (P - 1) * (P - 2) // 6
+    t1, n1 = DYN.find_dynamically_feasible_contacts(cp, cn, criterion="qp", tol=1e-4, first=0, last=total // 2)
+    t2, n2 = DYN.find_dynamically_feasible_contacts(cp, cn, criterion="qp", tol=1e-4, first=total // 2)
+    assert n1 + n2 == n and {tuple(t) for t in t1.tolist()} | {tuple(t) for t in t2.tolist()} == got

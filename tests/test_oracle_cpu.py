@@ -233,3 +233,35 @@ def test_kernel_logic_is_clean_under_address_and_ub_sanitizers():
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert out.stdout.count(" ok") == 7, out.stdout
+
+
+def test_qp_solver_logic_on_host_matches_independent_solve():
+    """csrc/pg_qp.cuh (non-negative least squares in generator space, the code of the QP kernels) compiled for the host vs
+    SLSQP on the reference's (Q, G, h) formulation: random triples, closure-like triples, degenerate frames (n = z),
+    unnormalised / axis-aligned normals."""
+    from oracle import dynfeas as DF
+    so = os.path.join(ROOT, "tests", "hostsim", "libpg_hostsim.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-include", "cstdio",
+                           "-o", so, os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")])
+    H = C.CDLL(so)
+    H.hostsim_qp.restype = C.c_double
+    rng = np.random.RandomState(5)
+    n_feasible = 0
+    for t in range(250):
+        p = rng.uniform(-0.2, 0.2, (3, 3))
+        nrm = rng.randn(3, 3)
+        nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+        if t % 3 == 0:
+            nrm = p - p.mean(0)
+            nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+        if t % 7 == 0:
+            nrm[0] = [0, 0, 1.0]
+        if t % 11 == 0:
+            nrm = np.round(nrm * 2) / 2
+            nrm[np.linalg.norm(nrm, axis=1) == 0] = [1, 0, 0]
+        it = C.c_int(0)
+        got = H.hostsim_qp(p.ctypes.data_as(C.c_void_p), nrm.ctypes.data_as(C.c_void_p), C.c_double(5.0), C.c_double(1.0), C.byref(it))
+        ref = DF.qp_objective(p, nrm, normalise=False)
+        assert abs(got - ref) <= 1e-6 * max(1.0, ref) + 2e-9, (t, got, ref, it.value)
+        n_feasible += got <= 1e-4
+    assert 50 < n_feasible < 250            # both outcomes are exercised
