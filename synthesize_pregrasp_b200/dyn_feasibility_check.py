@@ -71,6 +71,15 @@ def check_dyn_feasible(contact_points, contact_normals, tol=2e-3, count=None, de
     return (res, o) if return_objective else res
 
 
+def triple_range(rank, world_size, n_points):
+    """[first, last) of the lexicographic triple index space C(n_points, 3) owned by `rank` of `world_size` GPUs: contiguous,
+    disjoint, covering, sizes differing by at most one (no collective except the final count / gather)."""
+    total = n_points * (n_points - 1) * (n_points - 2) // 6
+    base, rem = divmod(total, world_size)
+    first = rank * base + min(rank, rem)
+    return first, first + base + (1 if rank < rem else 0)
+
+
 def find_dynamically_feasible_contacts(points, normals, min_dist=MIN_DISTANCE_BETWEEN_FINGER, first=0, last=None,
                                        max_out=1 << 22, device=None, criterion="simple", tol=1e-4):
     """All index triples (i<j<k) of the cloud passing the pairwise-distance prefilter (:260-265) and the closure test;
@@ -84,6 +93,10 @@ def find_dynamically_feasible_contacts(points, normals, min_dist=MIN_DISTANCE_BE
     nt = torch.as_tensor(np.asarray(normals, np.float64), device=dev).contiguous()
     P = pt.shape[0]
     total = P * (P - 1) * (P - 2) // 6
+    if last is None and first == 0:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():         # one slice of the index space per rank
+            first, last = triple_range(dist.get_rank(), dist.get_world_size(), P)
     last = total if last is None else min(last, total)
     out = torch.empty((max_out, 3), dtype=torch.int32, device=dev)
     cnt = torch.zeros(1, dtype=torch.int64, device=dev)

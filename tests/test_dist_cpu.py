@@ -40,3 +40,17 @@ def test_two_rank_merge_matches_single_process_update():
     res = sorted(q.get(timeout=120) for _ in ps)
     [p.join(60) for p in ps]
     assert all(e <= 1e-13 for _, e in res), res
+
+
+def test_triple_index_space_partition():
+    """The feasibility sweeps shard the C(P,3) triple index space across ranks: contiguous, disjoint, covering."""
+    from synthesize_pregrasp_b200.dyn_feasibility_check import triple_range
+    for P in (3, 14, 256, 1024):
+        total = P * (P - 1) * (P - 2) // 6
+        for world in (1, 2, 3, 8):
+            edges = [triple_range(r, world, P) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == total
+            for (a0, a1), (b0, b1) in zip(edges[:-1], edges[1:]):
+                assert a1 == b0 and a0 <= a1
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
