@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <atomic>
 #include <vector>
+#include <algorithm>
 #include "pg_internal.h"
 #include "pg_envbuild.h"
 
@@ -94,6 +95,29 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   size_t o_w1 = b.add(W.conv1_w, C1 * 4 * 4), o_b1 = b.add(W.conv1_b, C1 * 4);
   size_t o_w3hi = b.add(w3hi.data(), w3hi.size() * 4), o_w3lo = b.add(w3lo.data(), w3lo.size() * 4);
   size_t o_tri = sp->n_dist_tri > 0 ? b.add(sp->dist_tri, sizeof(double) * 9 * sp->n_dist_tri) : 0;
+  std::vector<double> tri_sph((size_t)4 * (sp->n_dist_tri > 0 ? sp->n_dist_tri : 0));
+  for (int t = 0; t < sp->n_dist_tri; t++) {
+    const double* v = sp->dist_tri + 9 * t;
+    double c[3], r2 = 0;
+    for (int k = 0; k < 3; k++) c[k] = (v[k] + v[3 + k] + v[6 + k]) / 3.0;
+    for (int q = 0; q < 3; q++) { double dd = 0; for (int k = 0; k < 3; k++) dd += (v[3 * q + k] - c[k]) * (v[3 * q + k] - c[k]); if (dd > r2) r2 = dd; }
+    tri_sph[4 * t] = c[0]; tri_sph[4 * t + 1] = c[1]; tri_sph[4 * t + 2] = c[2]; tri_sph[4 * t + 3] = sqrt(r2) * (1.0 + 1e-12);
+  }
+  size_t o_sph = sp->n_dist_tri > 0 ? b.add(tri_sph.data(), sizeof(double) * tri_sph.size()) : 0;
+  const int TG = 16, n_grp = (sp->n_dist_tri + TG - 1) / TG;
+  std::vector<double> grp_sph((size_t)4 * n_grp);
+  for (int g = 0; g < n_grp; g++) {
+    int t0 = g * TG, t1 = std::min(sp->n_dist_tri, t0 + TG);
+    double c[3] = {0, 0, 0}, r = 0;
+    for (int t = t0; t < t1; t++) for (int k = 0; k < 3; k++) c[k] += tri_sph[4 * t + k] / (t1 - t0);
+    for (int t = t0; t < t1; t++) for (int q = 0; q < 3; q++) {
+      double dd = 0;
+      for (int k = 0; k < 3; k++) dd += (sp->dist_tri[9 * t + 3 * q + k] - c[k]) * (sp->dist_tri[9 * t + 3 * q + k] - c[k]);
+      if (sqrt(dd) > r) r = sqrt(dd);
+    }
+    grp_sph[4 * g] = c[0]; grp_sph[4 * g + 1] = c[1]; grp_sph[4 * g + 2] = c[2]; grp_sph[4 * g + 3] = r * (1.0 + 1e-12);
+  }
+  size_t o_gsph = n_grp > 0 ? b.add(grp_sph.data(), sizeof(double) * grp_sph.size()) : 0;
   unsigned char* d = nullptr;
   cudaError_t ce = cudaMalloc(&d, b.h.size());
   if (ce != cudaSuccess) { delete e; return cuda_fail(ce, "cudaMalloc(env constants)"); }
@@ -114,6 +138,8 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   memcpy(c.crop, sp->crop, sizeof(c.crop));
   memcpy(c.dist_box, sp->dist_box, sizeof(c.dist_box));
   c.dist_tri = sp->n_dist_tri > 0 ? reinterpret_cast<const double*>(d + o_tri) : nullptr;
+  c.tri_sphere = sp->n_dist_tri > 0 ? reinterpret_cast<const double*>(d + o_sph) : nullptr;
+  c.tri_group_sphere = n_grp > 0 ? reinterpret_cast<const double*>(d + o_gsph) : nullptr;
   c.clearance_h = sp->clearance_h; c.project_uses_clearance = sp->project_uses_clearance;
   c.clear_n = sp->n_clear_walls;
   for (int w = 0; w < sp->n_clear_walls && w < 2; w++) {

@@ -9,6 +9,7 @@
 // point; (ii) conv3(concat(x, g)) = W3a x + W3b g with the g half evaluated once per cloud; (iii) cropped
 // points are masked to -inf before both max-pools; [P,256] activations never leave the SM.
 #include "pg_internal.h"
+#include "pg_cost_geom.cuh"
 
 namespace pg {
 
@@ -41,45 +42,6 @@ __device__ __forceinline__ float box_dist(double x, double y, double z, const do
   return (float)(outside > 0 ? outside : fmax(inside, 0.0));
 }
 
-__device__ double tri_dist2(double px, double py, double pz, const double* t) {
-  // squared distance from p to triangle (a,b,c), Ericson "Real-Time Collision Detection" 5.1.5
-  double ax = t[0], ay = t[1], az = t[2], bx = t[3], by = t[4], bz = t[5], cx = t[6], cy = t[7], cz = t[8];
-  double abx = bx - ax, aby = by - ay, abz = bz - az, acx = cx - ax, acy = cy - ay, acz = cz - az;
-  double apx = px - ax, apy = py - ay, apz = pz - az;
-  double d1 = abx * apx + aby * apy + abz * apz, d2 = acx * apx + acy * apy + acz * apz;
-  double qx, qy, qz;
-  if (d1 <= 0 && d2 <= 0) { qx = ax; qy = ay; qz = az; }
-  else {
-    double bpx = px - bx, bpy = py - by, bpz = pz - bz;
-    double d3 = abx * bpx + aby * bpy + abz * bpz, d4 = acx * bpx + acy * bpy + acz * bpz;
-    if (d3 >= 0 && d4 <= d3) { qx = bx; qy = by; qz = bz; }
-    else {
-      double vc = d1 * d4 - d3 * d2;
-      if (vc <= 0 && d1 >= 0 && d3 <= 0) { double v = d1 / (d1 - d3); qx = ax + v * abx; qy = ay + v * aby; qz = az + v * abz; }
-      else {
-        double cpx = px - cx, cpy = py - cy, cpz = pz - cz;
-        double d5 = abx * cpx + aby * cpy + abz * cpz, d6 = acx * cpx + acy * cpy + acz * cpz;
-        if (d6 >= 0 && d5 <= d6) { qx = cx; qy = cy; qz = cz; }
-        else {
-          double vb = d5 * d2 - d1 * d6;
-          if (vb <= 0 && d2 >= 0 && d6 <= 0) { double w = d2 / (d2 - d6); qx = ax + w * acx; qy = ay + w * acy; qz = az + w * acz; }
-          else {
-            double va = d3 * d6 - d5 * d4;
-            if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
-              double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
-              qx = bx + w * (cx - bx); qy = by + w * (cy - by); qz = bz + w * (cz - bz);
-            } else {
-              double den = 1.0 / (va + vb + vc), v = vb * den, w = vc * den;
-              qx = ax + abx * v + acx * w; qy = ay + aby * v + acy * w; qz = az + abz * v + acz * w;
-            }
-          }
-        }
-      }
-    }
-  }
-  double ex = px - qx, ey = py - qy, ez = pz - qz;
-  return ex * ex + ey * ey + ez * ez;
-}
 
 // h1 = relu(conv1) for one point; FROM_POSE uses the precomputed xyz part
 template <bool FROM_POSE>
@@ -154,9 +116,7 @@ pcn_kernel(CostDev cd, const double* __restrict__ pose, const double* __restrict
         float d = INFINITY;
         for (int b = 0; b < cd.n_dist_box; b++) d = fminf(d, box_dist(qx, qy, qz, cd.dist_box[b][0], cd.dist_box[b][1]));
         if (cd.n_dist_tri > 0) {
-          double best = INFINITY;
-          for (int t = 0; t < cd.n_dist_tri; t++) best = fmin(best, tri_dist2(qx, qy, qz, cd.dist_tri + 9 * t));
-          d = fminf(d, (float)sqrt(best));
+          d = tri_field(cd, qx, qy, qz, d);
         }
         s.df[p] = d;
         s.msk[p] = keep ? 0.f : -INFINITY;
@@ -487,7 +447,7 @@ int launch_mlp(PgEnv* env, const float* latent, int B, float* logit, cudaStream_
 }
 
 int launch_cost(PgEnv* env, const double* pose, const double* fins, int B, float* latent, float* logit, cudaStream_t st) {
-  if (env->use_tensor_cores && env->cost.n_dist_tri == 0) {
+  if (env->use_tensor_cores) {
     int rc = launch_cost_tc(env, pose, fins, B, latent, st);
     if (rc) return rc;
     return launch_mlp(env, latent, B, logit, st);

@@ -11,6 +11,7 @@
 // Operands sit in shared memory in the no-swizzle K-major canonical layout ([k-chunk of 16 B][row][16 B]:
 // SBO = 128 B between 8-row groups, LBO = rows*16 B between the two 16-byte halves of one K=8 step).
 #include "pg_internal.h"
+#include "pg_cost_geom.cuh"
 
 namespace pg {
 
@@ -215,6 +216,7 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
       double qx = (double)(float)wx, qy = (double)(float)wy, qz = (double)(float)wz;
       float d = INFINITY;
       for (int b = 0; b < cd.n_dist_box; b++) d = fminf(d, tc_box_dist(qx, qy, qz, cd.dist_box[b][0], cd.dist_box[b][1]));
+      if (cd.n_dist_tri > 0) d = tri_field(cd, qx, qy, qz, d);
       s.df[p] = d;
       s.msk[p] = keep ? 1 : 0;
       cnt += keep;

@@ -28,6 +28,8 @@ struct CostDev {                 // device pointers of the cost stage constants
   double crop[2][2][3];
   double dist_box[4][2][3];
   const double* dist_tri;
+  const double* tri_sphere;      // [n_dist_tri][4]: centroid and radius of each triangle's bounding sphere
+  const double* tri_group_sphere; // [ceil(n_dist_tri/16)][4]: bounding sphere of each group of 16 consecutive triangles
   double clearance_h;
   int project_uses_clearance;     // 1: checkClearance(local point) incl. the walls (bookshelf_graph_env.py:683-689)
   int clear_n;
