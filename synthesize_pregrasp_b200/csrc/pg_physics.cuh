@@ -63,6 +63,7 @@ struct Sim {
   V3 plo[2], phi[2];     // tight AABB each tip's broadphase proxy was last (re)created with
   int obj_first;         // reset substep: object proxy is older than the walls'
   int last_iterations;
+  int sync_cta;          // hull kernel: all threads of the CTA run rollouts, so substeps may start on a CTA barrier
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -940,6 +941,14 @@ PG_HD void integrate(const EnvDev& E, Sim& S) {
 
 template <int SHAPE>
 PG_HDN void substep(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, double* sm, int ss) {
+#if defined(__CUDA_ARCH__)
+  // The hull kernel stalls on instruction fetch: ~15 k rarely-executed instructions of collision code per substep, missed
+  // separately by every warp that reaches them at a different time.  All rollouts run the same number of substeps, so the
+  // warps of a CTA are lined up here and take those misses together.
+#if defined(PG_SUBSTEP_BARRIER)
+  if (S.sync_cta) __syncthreads();
+#endif
+#endif
   collide<SHAPE>(E, S, statR);
   apply_external(E, S);
   solve(E, S, statR, rs, sm, ss);

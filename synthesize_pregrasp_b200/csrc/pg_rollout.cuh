@@ -147,6 +147,7 @@ struct RolloutOut {
   double* trace;      // optional [N*SKIP][7]: pose at the START of every control substep (model_test.py:124-135)
   int* iters;         // optional [N*SKIP]
   int* settle_iters;  // optional [settle_substeps] (host diagnostics only)
+  int sync_cta;       // device: every thread of this CTA runs a rollout in this pass (see substep)
 };
 
 // sm / ss: the thread's on-chip solver slice (element i at sm[i*ss]); SM_DOUBLES elements
@@ -176,7 +177,7 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
       t.half = V3(E.tip_half[f][0], E.tip_half[f][1], E.tip_half[f][2]); t.friction = E.tip_friction;
     }
   }
-  S.nman = 0; S.filter_off = 0; S.obj_first = 1; S.last_iterations = 0; S.early = 0;
+  S.nman = 0; S.filter_off = 0; S.obj_first = 1; S.last_iterations = 0; S.early = 0; S.sync_cta = out.sync_cta;
   for (int f = 0; f < 2; f++) { S.plo[f] = V3(); S.phi[f] = V3(); }
   S.cons[0].active = 0; S.cons[1].active = 0;
   substep<SHAPE>(E, S, statR, rs, sm, ss);                                                       // :237

@@ -1,7 +1,9 @@
 // The rollout kernel template (one thread per rollout); instantiated for box objects in pg_rollout.cu and for hull objects
 // in pg_rollout_hull.cu -- two translation units because they are compiled with different floating-point contraction.
 #pragma once
+#ifndef PG_BLOCK_THREADS
 #define PG_BLOCK_THREADS 64
+#endif
 #include <cstdlib>
 #include "pg_internal.h"
 #include "pg_rollout.cuh"
@@ -26,7 +28,10 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const
     __syncthreads();
   }
   // grid-stride over the batch: the host may launch fewer CTAs than K/64 to cap how many rollouts are resident
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+  for (int k0 = blockIdx.x * blockDim.x; k0 < K; k0 += gridDim.x * blockDim.x) {
+    const int k = k0 + threadIdx.x;
+    const int cta_full = (k0 + (int)blockDim.x <= K);          // uniform over the CTA
+    if (k >= K) continue;
     RolloutOut out;
     out.pose = pose + (size_t)k * N * 7;
     out.fins = fins + (size_t)k * N * NFING * 3;
@@ -34,6 +39,7 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const
     out.trace = trace ? trace + (size_t)k * N * SKIP * 7 : nullptr;
     out.iters = iters ? iters + (size_t)k * N * SKIP : nullptr;
     out.settle_iters = nullptr;
+    out.sync_cta = cta_full;
     // several independent MPPI problems may share a launch: rollout k then uses the controls and the path of problem prob[k]
     const int q = prob ? prob[k] : 0;
     rollout_one<SHAPE>(*env, u + (size_t)q * N * ADIM, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path + (size_t)q * N, max_force, 1, out, nullptr, 0);   // solver slice: dynamic shared memory, see PG_SM
