@@ -950,6 +950,9 @@ PG_HDN void substep(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, double
 #endif
 #endif
   collide<SHAPE>(E, S, statR);
+#if defined(__CUDA_ARCH__) && defined(PG_SUBSTEP_BARRIER2)
+  if (S.sync_cta) __syncthreads();
+#endif
   apply_external(E, S);
   solve(E, S, statR, rs, sm, ss);
   integrate(E, S);
