@@ -477,7 +477,15 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
     double ta = bs_radius(E, m.a) * E.breaking_factor, tb = bs_radius(E, m.b) * E.breaking_factor;
     m.breaking = ta < tb ? ta : tb;
   }
-  for (int k = 0; k < S.nman; k++) {
+  for (int k = 0;; k++) {
+    const bool live = k < S.nman;
+#if defined(__CUDA_ARCH__) && defined(PG_SUBSTEP_BARRIER)
+    if (S.sync_cta) { if (!__syncthreads_or(live)) break; }     // narrowphase queries of the CTA start together (as in substep)
+    else if (!live) break;
+    if (!live) continue;
+#else
+    if (!live) break;
+#endif
     Manifold& m = S.man[k];
     Sink sink;
     sink.m = &m; sink.posA = bv[m.a].pos; sink.posB = bv[m.b].pos; sink.RA = bv[m.a].R; sink.RB = bv[m.b].R;
@@ -944,13 +952,14 @@ PG_HDN void substep(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, double
 #if defined(__CUDA_ARCH__)
   // The hull kernel stalls on instruction fetch: ~15 k rarely-executed instructions of collision code per substep, missed
   // separately by every warp that reaches them at a different time.  All rollouts run the same number of substeps, so the
-  // warps of a CTA are lined up here and take those misses together.
+  // warps of a CTA are lined up here, before every narrowphase query (collide) and before the solver set-up, and take
+  // those misses together.
 #if defined(PG_SUBSTEP_BARRIER)
   if (S.sync_cta) __syncthreads();
 #endif
 #endif
   collide<SHAPE>(E, S, statR);
-#if defined(__CUDA_ARCH__) && defined(PG_SUBSTEP_BARRIER2)
+#if defined(__CUDA_ARCH__) && defined(PG_SUBSTEP_BARRIER)
   if (S.sync_cta) __syncthreads();
 #endif
   apply_external(E, S);

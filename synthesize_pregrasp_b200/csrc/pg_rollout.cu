@@ -30,6 +30,8 @@ int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N
   }
   const size_t smem = SM_DOUBLES * RK_THREADS * sizeof(double);
   if (blocks > ctas_per_sm * n_sm) blocks = ctas_per_sm * n_sm;
+  static bool optin = false;                                   // CTA shapes whose slice exceeds the 48 KB default (tuning builds)
+  if (smem > 48 * 1024 && !optin) { PG_CUDA(cudaFuncSetAttribute(rollout_kernel<SHAPE_BOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); optin = true; }
   if (env->host_env.obj_shape != SHAPE_BOX)
     launch_rollout_hull(blocks, threads, smem, st, env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters, prob_dev);
   else

@@ -2,10 +2,11 @@
 // rounds every product, and the GJK / expanding-polytope decisions (support ties, near-equal depths, simplex region
 // tests) turn a 1-ulp difference into a different contact point; without contraction the kernel agrees with the
 // CPU restatement to 1e-12 on 42/48 random plate rollouts (23/48 with contraction).  ~15 % slower, by choice.
-// CTA shape of the hull kernel: ONE large CTA per SM whose warps meet on a barrier at the start of every substep.  The kernel
-// stalls on instruction fetch (profiles/README.md): each substep walks ~15 k rarely-executed instructions of collision code,
-// and warps that reach them at different times each pay the misses.  All rollouts run the same number of substeps, so the
-// barrier is free of deadlock and lines the warps up: 2108 -> 1440 ms on the plate workload (64-thread CTAs: no effect).
+// CTA shape of the hull kernel: ONE large CTA per SM whose warps meet on CTA barriers inside every substep (at its start,
+// before each narrowphase query, before the solver set-up).  The kernel stalls on instruction fetch (profiles/README.md):
+// each substep walks ~15 k rarely-executed instructions of collision code, and warps that reach them at different times
+// each pay the misses.  All rollouts run the same number of substeps, so the barriers are free of deadlock and line the
+// warps up: 2108 -> 1440 ms on the plate workload with the first barrier, 1110 ms with all three (64-thread CTAs: no effect).
 #define PG_SUBSTEP_BARRIER 1
 #ifndef PG_BLOCK_THREADS
 #define PG_BLOCK_THREADS 448
