@@ -157,6 +157,7 @@ extern "C" int pg_env_destroy(PgEnv* e) {
   cudaSetDevice(e->device);
   cudaFree(e->blob); cudaFree(e->pose); cudaFree(e->fins); cudaFree(e->logit); cudaFree(e->latent); cudaFree(e->path_dev);
   cudaFree(e->u_stage); cudaFree(e->noise_stage); cudaFree(e->J_stage); cudaFree(e->metric_stage); cudaFree(e->trace_stage);
+  cudaFree(e->regroup);
   delete e;
   return PG_OK;
 }

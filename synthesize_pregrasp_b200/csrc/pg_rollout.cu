@@ -6,36 +6,37 @@
 // latency on every row; a thread per rollout keeps all 32 lanes busy with independent rollouts and the only
 // divergence is the per-rollout row count.  HBM sees u + noise in and pose/fins/metric out; everything else
 // (bodies, manifolds, solver rows) lives in registers and thread-local memory for the whole rollout.
+//
+// CTA shape (pg_rollout_kernel.cuh): ONE 448-thread CTA per SM.  Its warps meet on CTA barriers inside every substep so that
+// they walk the collision code together (instruction fetch), and before the settle phase the CTA re-deals its rollouts to
+// its threads by solver work (settle_regroup, pg_rollout.cuh) so that a warp holds rollouts of one kind: bookshelf physics
+// 1425 -> 1268 ms with the regrouping, 1210 ms with the barriers as well (64-thread CTAs, 7 per SM, before).
 #include "pg_rollout_kernel.cuh"
 
 namespace pg {
 
 // defined in pg_rollout_hull.cu (compiled without FMA contraction: GJK / polytope decisions are rounding-sensitive)
-void launch_rollout_hull(int blocks, int threads, size_t smem, cudaStream_t st, const EnvDev* env, const double* u, const float* noise,
-                         int K, int N, const int* path, double max_force, double* pose, double* fins, double* metric, double* trace, int* iters,
-                         const int* prob);
+int launch_rollout_hull(cudaStream_t st, const EnvDev* env, const double* u, const float* noise, int K, int N, const int* path, double max_force,
+                        double* pose, double* fins, double* metric, double* trace, int* iters, const int* prob, void* regroup);
 
 int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
                    double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st, const int* prob_dev) {
-  const int threads = RK_THREADS;
-  int blocks = (K + threads - 1) / threads;
-  // Resident CTAs per SM: the solver rows of all resident rollouts (2-3 KB each) are re-read every Gauss-Seidel
-  // iteration; the grid can be capped below K/64 (grid-stride kernel) to keep that working set nearer the 126 MB L2.
-  // PG_ROLLOUT_CTAS overrides (tuning only).
-  static int ctas_per_sm = -1, n_sm = 0;
-  if (ctas_per_sm < 0) {
-    const char* e = getenv("PG_ROLLOUT_CTAS"); ctas_per_sm = e ? atoi(e) : RK_MINBLOCKS;
-    if (ctas_per_sm < 1 || ctas_per_sm > RK_MINBLOCKS) ctas_per_sm = RK_MINBLOCKS;
-    int dev = 0; PG_CUDA(cudaGetDevice(&dev)); PG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  // exchange buffer of the settle-phase regrouping (pg_rollout.cuh), one slot per rollout
+  const size_t need = (size_t)K * sizeof(RegroupSlot);
+  if (env->cap_regroup < need) {
+    cudaFree(env->regroup); env->regroup = nullptr; env->cap_regroup = 0;
+    PG_CUDA(cudaMalloc(&env->regroup, need));
+    env->cap_regroup = need;
   }
-  const size_t smem = SM_DOUBLES * RK_THREADS * sizeof(double);
-  if (blocks > ctas_per_sm * n_sm) blocks = ctas_per_sm * n_sm;
-  static bool optin = false;                                   // CTA shapes whose slice exceeds the 48 KB default (tuning builds)
-  if (smem > 48 * 1024 && !optin) { PG_CUDA(cudaFuncSetAttribute(rollout_kernel<SHAPE_BOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); optin = true; }
+  static int use_regroup = -1;                                 // PG_REGROUP=0 switches the regrouping off (tuning only)
+  if (use_regroup < 0) { const char* v = getenv("PG_REGROUP"); use_regroup = (v && atoi(v) == 0) ? 0 : 1; }
+  void* regroup = use_regroup ? env->regroup : nullptr;
+  int rc;
   if (env->host_env.obj_shape != SHAPE_BOX)
-    launch_rollout_hull(blocks, threads, smem, st, env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters, prob_dev);
+    rc = launch_rollout_hull(st, env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters, prob_dev, regroup);
   else
-    rollout_kernel<SHAPE_BOX><<<blocks, threads, smem, st>>>(env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters, prob_dev);
+    rc = launch_rollout_sized<SHAPE_BOX>(st, env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters, prob_dev, regroup);
+  if (rc) return rc;
   count_launch();
   PG_CUDA(cudaGetLastError());
   return PG_OK;

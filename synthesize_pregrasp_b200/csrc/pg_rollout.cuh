@@ -148,7 +148,45 @@ struct RolloutOut {
   int* iters;         // optional [N*SKIP]
   int* settle_iters;  // optional [settle_substeps] (host diagnostics only)
   int sync_cta;       // device: every thread of this CTA runs a rollout in this pass (see substep)
+  void* regroup;      // device: [K] RegroupSlot exchange buffer, or null (see settle_regroup)
+  int k;              // device: index of this rollout in the batch
 };
+
+// Settle-phase regrouping (device only).  The warp pays for its slowest lane: a rollout whose contact solver stops at the
+// residual threshold after ~7 sweeps waits for lanes that run all 50, and which kind a rollout is hardly changes once the
+// fingers hold still.  Before the settle substeps (49-74 % of a rollout) the rollouts of a CTA are therefore re-dealt to
+// its threads in order of the solver work they needed during the last control phase, so that warps hold rollouts of one
+// kind.  The state travels through a global exchange buffer (5 KB per rollout, once); results are unchanged bit for bit
+// because a rollout's arithmetic does not depend on the thread that runs it.
+struct RegroupSlot {
+  Sim S;
+  double m0;
+  double* pose;
+  double* metric;
+};
+
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ void settle_regroup(Sim& S, double& m0, RolloutOut& out, int key) {
+  RegroupSlot* slots = (RegroupSlot*)out.regroup;
+  int* keys = (int*)pg_solver_sm;                 // the solver slices are dead between substeps
+  int* src = keys + blockDim.x;
+  const int me = threadIdx.x, n = blockDim.x;
+  __syncthreads();                                // every thread has left its last solve
+  RegroupSlot& mine = slots[out.k];
+  mine.S = S; mine.m0 = m0; mine.pose = out.pose; mine.metric = out.metric;
+  keys[me] = key;
+  __syncthreads();
+  int rank = 0;
+  for (int j = 0; j < n; j++) { const int kj = keys[j]; rank += (kj < key || (kj == key && j < me)) ? 1 : 0; }
+  src[rank] = me;
+  __syncthreads();
+  const int from = src[me];
+  const RegroupSlot& theirs = slots[out.k - me + from];
+  S = theirs.S; m0 = theirs.m0; out.pose = theirs.pose; out.metric = theirs.metric;
+  out.k = out.k - me + from;
+  __syncthreads();                                // keys / src are overwritten by the next solve
+}
+#endif
 
 // sm / ss: the thread's on-chip solver slice (element i at sm[i*ss]); SM_DOUBLES elements
 template <int SHAPE>
@@ -214,6 +252,7 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
       }
     }
     // ---- servo loop :504-533
+    int solver_work = 0;                            // regroup key: solver sweeps of this control phase
     for (int t = 0; t < SKIP; t++) {
       DynBody& o = S.dyn[0];
       if (out.trace) {
@@ -230,10 +269,19 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
       }
       substep<SHAPE>(E, S, statR, rs, sm, ss);
       if (out.iters) out.iters[j * SKIP + t] = S.last_iterations;
+      solver_work += S.last_iterations;
+    }
+    for (int i = 0; i < NFING; i++) {
+      out.fins[(j * NFING + i) * 3 + 0] = cur_pos[i].x;
+      out.fins[(j * NFING + i) * 3 + 1] = cur_pos[i].y;
+      out.fins[(j * NFING + i) * 3 + 2] = cur_pos[i].z;
     }
     // ---- settle + metric :556-603 (train mode)
     if (j == N - 1 && train) {
       double m0 = (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
+#if defined(__CUDA_ARCH__)
+      if (out.regroup) settle_regroup(S, m0, out, solver_work);     // from here on this thread may run another rollout of its CTA
+#endif
       for (int s = 0; s < E.settle_substeps; s++) {
         substep<SHAPE>(E, S, statR, rs, sm, ss);
         if (out.settle_iters) out.settle_iters[s] = S.last_iterations;
@@ -243,11 +291,6 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
     DynBody& o = S.dyn[0];
     double* p = out.pose + j * 7;
     p[0] = o.pos.x; p[1] = o.pos.y; p[2] = o.pos.z; p[3] = o.q.x; p[4] = o.q.y; p[5] = o.q.z; p[6] = o.q.w;
-    for (int i = 0; i < NFING; i++) {
-      out.fins[(j * NFING + i) * 3 + 0] = cur_pos[i].x;
-      out.fins[(j * NFING + i) * 3 + 1] = cur_pos[i].y;
-      out.fins[(j * NFING + i) * 3 + 2] = cur_pos[i].z;
-    }
   }
 }
 
