@@ -261,7 +261,7 @@ def main():
     ach_hbm = bytes_phys / (phys_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_kernel launch at K = 65536 (ncu, profiles/r1d_sections_*.csv);
     # scaled linearly in K for other batch sizes of the same workload, null for workloads that were not captured
-    NCU_TRAFFIC_K65536 = {"bookshelf": 4723434166528 + 788487916288, "plate": 1404046660352 + 840271186944}
+    NCU_TRAFFIC_K65536 = {"bookshelf": 2477255991040 + 509152934912, "plate": 1404046660352 + 840271186944}
     traffic = NCU_TRAFFIC_K65536.get(wl["env"])
     traffic = None if traffic is None else traffic * (K / 65536.0)
     roof = {"kernel": "rollout_kernel (physics, %.0f%% of the step)" % (100 * phys_ms / (phys_ms + cost_ms)), "bound": "hbm",

@@ -23,15 +23,18 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const
                                                       const int* __restrict__ path, double max_force,
                                                       double* __restrict__ pose, double* __restrict__ fins,
                                                       double* __restrict__ metric, double* __restrict__ trace,
-                                                      int* __restrict__ iters, const int* __restrict__ prob, void* regroup) {
+                                                      int* __restrict__ iters, const int* __restrict__ prob, void* regroup, int lanes) {
   if (SHAPE == SHAPE_HULL) {
     for (int i = threadIdx.x; i < 3 * env->n_hull; i += blockDim.x) pg_hull_sm[i] = env->hull[i];
     __syncthreads();
   }
-  // grid-stride over the batch: the host may launch fewer CTAs than K/64 to cap how many rollouts are resident
-  for (int k0 = blockIdx.x * blockDim.x; k0 < K; k0 += gridDim.x * blockDim.x) {
-    const int k = k0 + threadIdx.x;
-    const int cta_full = (k0 + (int)blockDim.x <= K);          // uniform over the CTA
+  // `lanes` rollouts per warp (small batches leave lanes empty so that every SM has a warp); the other lanes leave at once
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, per_cta = (blockDim.x >> 5) * lanes;
+  if (lane >= lanes) return;
+  // grid-stride over the batch
+  for (int k0 = blockIdx.x * per_cta; k0 < K; k0 += gridDim.x * per_cta) {
+    const int k = k0 + warp * lanes + lane;
+    const int cta_full = (k0 + per_cta <= K);                  // uniform over the CTA: all its remaining threads run a rollout
     if (k >= K) continue;
     RolloutOut out;
     out.pose = pose + (size_t)k * N * 7;
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const
     out.iters = iters ? iters + (size_t)k * N * SKIP : nullptr;
     out.settle_iters = nullptr;
     out.sync_cta = cta_full;
-    out.regroup = (cta_full && blockDim.x > 32) ? regroup : nullptr;
+    out.regroup = (cta_full && lanes == 32 && blockDim.x > 32) ? regroup : nullptr;
     out.k = k;
     // several independent MPPI problems may share a launch: rollout k then uses the controls and the path of problem prob[k]
     const int q = prob ? prob[k] : 0;
@@ -50,8 +53,10 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const
 }
 
 // One CTA per SM, sized to the batch: the shared-memory slices are strided by the compile-time CTA size, so any launch size up
-// to it is valid; small batches get smaller CTAs so that every SM has work (K = 360: 12 CTAs of 32; 30 x 360: 113 CTAs of 96;
-// K = 65 536: 147 CTAs of 448).
+// to it is valid.  A warp takes about as long with 1 rollout as with 32 (the sequential chain of one rollout; measured on the
+// plate: 297 vs 381 ms), and more warps per SM cost instruction fetch, so: one warp per SM first (K = 360: 120 warps of 3
+// rollouts, 300 ms instead of 381 ms with 12 full warps), then full lanes, then more warps per SM (30 x 360: 338 full warps;
+// K = 65 536: 147 CTAs of 448 threads).  Spreading 30 x 360 rollouts over 1800 warps of 6 lanes: 779 ms vs 553 ms.
 template <int SHAPE>
 static int launch_rollout_sized(cudaStream_t st, const EnvDev* env, const double* u, const float* noise, int K, int N, const int* path,
                                 double max_force, double* pose, double* fins, double* metric, double* trace, int* iters, const int* prob,
@@ -64,13 +69,19 @@ static int launch_rollout_sized(cudaStream_t st, const EnvDev* env, const double
     PG_CUDA(cudaFuncSetAttribute(rollout_kernel<SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PG_CUDA(cudaDeviceGetAttribute(&sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
   }
-  const int n_sm = sm_of[dev];
-  int threads = ((K + n_sm - 1) / n_sm + 31) / 32 * 32;
-  if (threads < 32) threads = 32;
-  if (threads > RK_THREADS) threads = RK_THREADS;
-  int blocks = (K + threads - 1) / threads;
+  const int n_sm = sm_of[dev], max_warps = RK_THREADS / 32;
+  int lanes = (K + n_sm - 1) / n_sm;                           // one warp per SM first, then fill its lanes, then add warps
+  static int lanes_env = -1;                                   // PG_LANES overrides (tuning only)
+  if (lanes_env < 0) { const char* v = getenv("PG_LANES"); lanes_env = v ? atoi(v) : 0; }
+  if (lanes_env > 0) lanes = lanes_env;
+  if (lanes < 1) lanes = 1;
+  if (lanes > 32) lanes = 32;
+  const int warps = (K + lanes - 1) / lanes;
+  int wpc = (warps + n_sm - 1) / n_sm;
+  if (wpc > max_warps) wpc = max_warps;
+  int blocks = (warps + wpc - 1) / wpc;
   if (blocks > RK_MINBLOCKS * n_sm) blocks = RK_MINBLOCKS * n_sm;
-  rollout_kernel<SHAPE><<<blocks, threads, smem, st>>>(env, u, noise, K, N, path, max_force, pose, fins, metric, trace, iters, prob, regroup);
+  rollout_kernel<SHAPE><<<blocks, 32 * wpc, smem, st>>>(env, u, noise, K, N, path, max_force, pose, fins, metric, trace, iters, prob, regroup, lanes);
   return PG_OK;
 }
 

@@ -342,19 +342,19 @@ def test_multi_problem_rollouts_equal_separate_problems(EN):
 @pytest.mark.parametrize("env,F", [("plate", 20.0), ("bookshelf", 50.0)])
 def test_settle_regrouping_does_not_change_results(EN, env, F):
     """Large batches re-deal the rollouts of a CTA to its threads before the settle phase (csrc/pg_rollout.cuh
-    settle_regroup); batches of <= 32 rollouts per SM do not.  A rollout's result must not depend on it: one launch of K
+    settle_regroup); batches that do not fill the lanes of 14 warps per SM do not.  A rollout's result must not depend on it: one launch of K
     rollouts == the same rollouts in small launches, bit for bit (cost J goes through pose and fingertip outputs)."""
     from synthesize_pregrasp_b200.envspec import make_spec
     spec = make_spec(env)
     eng = EN.RolloutEngine(spec, device=0)
     gen = torch.Generator(device="cuda:0").manual_seed(5)
     n_sm = torch.cuda.get_device_properties(0).multi_processor_count
-    K, N = n_sm * 96 + 5, 2                         # 128-thread CTAs, the last one partial
+    K, N = n_sm * 448 - 7, 2                        # full lanes, 448-thread CTAs, the last one partial (no regrouping there)
     u = 0.2 * torch.randn((N, 48), generator=gen, device="cuda:0", dtype=torch.float64)
     noise = 0.8 * torch.randn((K, N, 48), generator=gen, device="cuda:0", dtype=torch.float32)
     path = np.zeros(N, np.int32)
     J, metric = eng.rollout(u, noise, path, F, want_metric=True)
-    chunk = n_sm * 16
+    chunk = 8192
     for a in range(0, K, chunk):
         Jc, mc = eng.rollout(u, noise[a:a + chunk].contiguous(), path, F, want_metric=True)
         assert torch.equal(J[a:a + chunk], Jc) and torch.equal(metric[a:a + chunk], mc), a
