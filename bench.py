@@ -203,6 +203,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # timing rule: inputs + per-rollout state larger than the 126 MB L2, or an L2 flush between the timed steps
+    footprint_mb = K * (N_STEPS * D * 4 + 21408) / 1e6
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if footprint_mb <= 126 else None
+
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -212,6 +216,8 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
     for i in range(args.steps):
+        if flush_buf is not None:
+            flush_buf.fill_(i & 0xFF)            # 256 MB write = 2x L2; ~0.1 ms inside the timed region
         step_device()
         ev[i + 1].record()
     barrier()
@@ -259,9 +265,9 @@ def main():
     F64_PEAK_TF = 148 * 64 * 2 * 1.965e9 / 1e12     # nominal DFMA rate (half the fp32 lanes)
     bytes_phys = K * (N_STEPS * D * 4 + N_STEPS * (7 + 6) * 8 + 8) + N_STEPS * D * 8
     ach_hbm = bytes_phys / (phys_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_kernel launch at K = 65536 (ncu, profiles/r1d_sections_*.csv);
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_kernel launch at K = 65536 (ncu, profiles/r1g_sections_bookshelf_K65536.csv, r1h_sections_plate_K65536.csv);
     # scaled linearly in K for other batch sizes of the same workload, null for workloads that were not captured
-    NCU_TRAFFIC_K65536 = {"bookshelf": 2477255991040 + 509152934912, "plate": 1404046660352 + 840271186944}
+    NCU_TRAFFIC_K65536 = {"bookshelf": 2477255991040 + 509152934912, "plate": 1450118829824 + 820202471936}
     traffic = NCU_TRAFFIC_K65536.get(wl["env"])
     traffic = None if traffic is None else traffic * (K / 65536.0)
     roof = {"kernel": "rollout_kernel (physics, %.0f%% of the step)" % (100 * phys_ms / (phys_ms + cost_ms)), "bound": "hbm",
@@ -271,8 +277,9 @@ def main():
             "note": "algorithmic HBM bytes are ~400 B per rollout-step (u, noise in; pose, fins, metric out), so frac is tiny by "
                     "construction.  The measured traffic is 5 orders of magnitude above it: the per-rollout solver rows (2-3 KB, "
                     "thread-local memory) of all 66k resident rollouts exceed the 126 MB L2 and are re-read from HBM on every "
-                    "Gauss-Seidel iteration (L2 hit 24 %), which puts the kernel at ~60 % of HBM bandwidth with latency-bound "
-                    "warps (profiles/README.md).  Keeping those rows on chip is the next optimisation."}
+                    "Gauss-Seidel iteration (L2 hit 39 %), which puts the box kernel at ~40 % of HBM bandwidth with latency-bound "
+                    "warps (profiles/r1g_sections_bookshelf_K65536.csv, profiles/README.md).  Keeping those rows on chip is the "
+                    "next optimisation."}
     ach64 = FLOP_PER_SUBSTEP * substeps * K / (phys_ms * 1e-3) / 1e12
     roof64 = {"kernel": "rollout_kernel", "bound": "fp64-issue", "achieved": ach64, "peak": F64_PEAK_TF, "unit": "TFLOP/s",
               "frac": ach64 / F64_PEAK_TF, "peak_source": "nominal 148 SM x 64 DFMA/clk x 1.965 GHz"}
@@ -281,14 +288,23 @@ def main():
                  "unit": "TFLOP/s", "frac": ach_t / peaks["bf16"], "peak_source": peaks["src"],
                  "note": "3x-split tf32 counts 1x algorithmic FLOP; 41% of the algorithmic FLOPs (conv3 point half) run on tcgen05, "
                          "conv2/conv4/MLP on fp32 FFMA"}
-    cpu_n = args.cpu_sample or 64
+    # bounded sample of the same workload on one host core: a fixed count if --cpu-sample is given, else chunks until ~12 s
     ref = CpuReference(wl["env"], wl["force"], 1)
-    cpu_v, cpu_dt = ref.run(cpu_n)
+    if args.cpu_sample:
+        cpu_n = args.cpu_sample
+        cpu_v, cpu_dt = ref.run(cpu_n)
+    else:
+        cpu_n, cpu_dt = 0, 0.0
+        while cpu_dt < 12.0:
+            _, dt1 = ref.run(32, seed=cpu_n)
+            cpu_n += 32; cpu_dt += dt1
+        cpu_v = cpu_n * N_STEPS / cpu_dt
     line = {"metric": "rollout-steps/sec", "value": value, "unit": "rollout-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "env": wl["env"], "max_force": wl["force"], "K_per_gpu": K, "N": N_STEPS, "D": D,
-                       "substeps_per_rollout": substeps, "sigma": SIGMA, "l2": f"inputs+state {K * (N_STEPS * D * 4 + 21408) / 1e6:.0f} MB > 126 MB L2"},
+                       "substeps_per_rollout": substeps, "sigma": SIGMA, "l2": (f"inputs+state {footprint_mb:.0f} MB > 126 MB L2" if flush_buf is None else
+                              f"inputs+state {footprint_mb:.0f} MB < 126 MB L2: flushed by a 256 MB write before every timed step (inside the timed region)")},
             "substeps_per_s": K * world * substeps / (ms_per_step * 1e-3), "mppi_iters_per_s": 1e3 / ms_per_step,
             "stage_ms": {"physics": phys_ms, "cost": cost_ms},
             "roofline": roof, "roofline_fp64": roof64, "roofline_cost": roof_cost,
