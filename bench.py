@@ -261,7 +261,9 @@ def main():
     # u + noise in, pose/fins/metric out; neither the HBM nor the tensor roofline binds it (fp64 issue/latency bound),
     # so the schema object is given for HBM and the fp64 and tensor views are added beside it.
     FLOP_PER_EVAL = 164.9e6          # algorithmic FLOPs of one score evaluation at P=2048
-    FLOP_PER_SUBSTEP = 90e3          # SURVEY 8(d) estimate of one physics substep
+    # audited FLOPs of the solver rows per substep (tools/audit_substep_flops.py -> profiles/r1h_flop_audit.json; 1 FMA = 2,
+    # collision detection / integration not counted); SURVEY 8(d)'s 90 kFLOP estimate for workloads that were not audited
+    FLOP_PER_SUBSTEP = {"bookshelf": 66.6e3, "plate": 77.5e3, "waterbottle": 66.5e3, "foodbox": 97.8e3}.get(wl["env"], 90e3)
     F64_PEAK_TF = 148 * 64 * 2 * 1.965e9 / 1e12     # nominal DFMA rate (half the fp32 lanes)
     bytes_phys = K * (N_STEPS * D * 4 + N_STEPS * (7 + 6) * 8 + 8) + N_STEPS * D * 8
     ach_hbm = bytes_phys / (phys_ms * 1e-3) / 1e9
@@ -282,7 +284,8 @@ def main():
                     "next optimisation."}
     ach64 = FLOP_PER_SUBSTEP * substeps * K / (phys_ms * 1e-3) / 1e12
     roof64 = {"kernel": "rollout_kernel", "bound": "fp64-issue", "achieved": ach64, "peak": F64_PEAK_TF, "unit": "TFLOP/s",
-              "frac": ach64 / F64_PEAK_TF, "peak_source": "nominal 148 SM x 64 DFMA/clk x 1.965 GHz"}
+              "frac": ach64 / F64_PEAK_TF, "peak_source": "nominal 148 SM x 64 DFMA/clk x 1.965 GHz",
+              "flop_per_substep": FLOP_PER_SUBSTEP, "flop_source": "audited solver rows, profiles/r1h_flop_audit.json"}
     ach_t = FLOP_PER_EVAL * K * N_STEPS / (cost_ms * 1e-3) / 1e12
     roof_cost = {"kernel": "pcn_tc_kernel (fused cost, tcgen05 3xTF32)", "bound": "tensor", "achieved": ach_t, "peak": peaks["bf16"],
                  "unit": "TFLOP/s", "frac": ach_t / peaks["bf16"], "peak_source": peaks["src"],

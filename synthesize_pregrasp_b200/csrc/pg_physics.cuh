@@ -801,6 +801,13 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
 #define PG_PIN(x)
 #define PG_PIN3(v)
 #endif
+  // host-only FLOP audit of the Gauss-Seidel sweep (tools/audit_substep_flops.py); compiles to nothing in the CUDA build
+#if defined(PG_HOST_STATS) && !defined(__CUDA_ARCH__)
+  extern double g_stat_flops[4];
+#define PG_AUDIT(slot, n) g_stat_flops[slot] += (n)
+#else
+#define PG_AUDIT(slot, n)
+#endif
   const int nn = rs.nc.n;
   const double mi0 = max_imp[0], mi1 = max_imp[1];
   const int ncb0 = rs.nc.body[0], ncb1 = rs.nc.body[1];
@@ -850,6 +857,7 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
         else side_apply(sm, ss, d, cur.col, V3(), m_tip, delta);
         double res = delta * cur.den;            // = delta / inv, the velocity change of this row
         lsr = fmax(lsr, res * res);
+        PG_AUDIT(0, i < 3 ? 7 : 45);             // linear row: 7 flops; angular row: 12 (dot) + 28 (inertia product, axpy) + 5
         cur = nxt;
       }
     }
@@ -875,6 +883,7 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
         if (db >= 0) side_apply(sm, ss, db, tB, -n, db == 0 ? m_obj : m_tip, delta);
         double res = delta * cur.den;
         lsr = fmax(lsr, res * res);
+        PG_AUDIT(1, 25 + 40 * ((da >= 0) + (db >= 0)));   // 2 cross products + clamp, per dynamic side a 6-dot and an impulse application
         cur = nxt;
       }
     }
@@ -916,7 +925,9 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
       if (db >= 0) side_apply2(sm, ss, db, tB1 * dA + tB2 * dB, -(l1 * dA + l2 * dB), db == 0 ? m_obj : m_tip);
       double res = dA * den1 + dB * den2;
       lsr = fmax(lsr, res * res);
+      PG_AUDIT(2, 67 + 66 * ((da >= 0) + (db >= 0)));     // 4 cross products, cone clip, per dynamic side two 6-dots and one combined impulse
     }
+    PG_AUDIT(3, 1);                                       // iterations
     if (lsr <= E.residual_threshold || it >= E.iterations - 1) { it++; break; }
   }
   S.last_iterations = it;

@@ -6,7 +6,8 @@
 #include "../../synthesize_pregrasp_b200/csrc/pg_qp.cuh"
 
 #ifdef PG_HOST_STATS
-namespace pg { long g_stat_pts[32], g_stat_nc[16]; }
+namespace pg { long g_stat_pts[32], g_stat_nc[16]; double g_stat_flops[4]; }
+extern "C" void hostsim_flops(double* out, int reset) { for (int i = 0; i < 4; i++) { out[i] = pg::g_stat_flops[i]; if (reset) pg::g_stat_flops[i] = 0; } }
 extern "C" void hostsim_stats(long* pts, long* nc) { for (int i = 0; i < 32; i++) pts[i] = pg::g_stat_pts[i]; for (int i = 0; i < 16; i++) nc[i] = pg::g_stat_nc[i]; }
 #endif
 static int* g_settle = nullptr;
