@@ -231,6 +231,28 @@ def test_optimizer_api_runs_and_improves(EN):
     assert abs(-J - neg_jopt) <= 1e-9 * max(1.0, abs(J))
 
 
+def test_model_optimize_driver_serial_and_batched(EN, tmp_path):
+    """Host mirror of model_optimize.py:36-123 (paths x runs loops, output files), both schedules, tiny sizes."""
+    from synthesize_pregrasp_b200 import model_optimize as MO
+    base = ["--env", "foodbox", "--max_force", "20", "--has_distance_field", "--iters", "2", "--runs", "2", "--exp_name", "t"]
+    res = MO.run(MO.build_parser().parse_args(base + ["--out_dir", str(tmp_path / "serial")]))
+    assert len(res) == 1 and res[0]["uopt"].shape == (2, 48) and len(res[0]["Jopt_log"]) == 2
+    assert np.isfinite(res[0]["best"]) and res[0]["best"] >= res[0]["mean"] - 1e-9
+    for f in ("rewards/optimal_t_20.0.npy", "rewards/run_t_20.0.npy", "traj/t_20.0.npy", "log/t.txt"):
+        assert (tmp_path / "serial" / f).exists(), f
+    np.testing.assert_array_equal(np.load(tmp_path / "serial" / "traj" / "t_20.0.npy"), res[0]["uopt"])
+    # batched schedule: run j of the path is seeded like the serial run j, and every problem of a multi-problem launch
+    # reproduces its serial optimiser -> same best reward and controls
+    resb = MO.run(MO.build_parser().parse_args(base + ["--batched", "--out_dir", str(tmp_path / "batched")]))
+    assert len(resb) == 1 and abs(resb[0]["best"] - res[0]["best"]) <= 1e-9 * max(1.0, abs(res[0]["best"]))
+    np.testing.assert_allclose(resb[0]["uopt"], res[0]["uopt"], rtol=0, atol=1e-12)
+    # --validate takes its paths from paths_id.npy and the committed contact-state graph
+    resv = MO.run(MO.build_parser().parse_args(["--env", "plate", "--max_force", "20", "--has_distance_field", "--validate", "--iters", "1",
+                                                "--runs", "1", "--max_paths", "2", "--batched", "--exp_name", "v",
+                                                "--out_dir", str(tmp_path / "validate")]))
+    assert [r["path"] for r in resv] == [[1, 2], [1, 7]] and all(np.isfinite(r["best"]) for r in resv)
+
+
 def test_errors_are_reported_not_swallowed(EN):
     from synthesize_pregrasp_b200.envspec import make_spec
     import dataclasses

@@ -265,3 +265,19 @@ def test_qp_solver_logic_on_host_matches_independent_solve():
         assert abs(got - ref) <= 1e-6 * max(1.0, ref) + 2e-9, (t, got, ref, it.value)
         n_feasible += got <= 1e-4
     assert 50 < n_feasible < 250            # both outcomes are exercised
+
+
+def test_model_optimize_driver_arguments_and_paths():
+    """model_optimize.py:36-83: same argument names and defaults, path list from paths_id.npy under --validate."""
+    from synthesize_pregrasp_b200 import model_optimize as MO
+    a = MO.build_parser().parse_args(["--env", "plate", "--max_force", "20", "--has_distance_field", "--name_score", "x"])
+    assert (a.iters, a.steps, a.runs, a.validate, a.exp_name) == (20, 2, 3, False, "u_opt_0-10_tp4")
+    kw = MO.optimiser_kwargs(a, 20.0)
+    assert kw["Num_processes"] * kw["Traj_per_process"] == 360 and kw["sigma"] == 0.8 and kw["max_forces"] == 20.0
+    a.validate = True
+    assert MO.optimiser_kwargs(a, 20.0)["Traj_per_process"] == 15
+    assert MO.path_list("plate", 2, False, 10) == [[0, 0, 0]]
+    paths = MO.path_list("plate", 2, True, 10)
+    spec = make_spec("plate")
+    assert len(paths) == min(10, len(spec.paths_id)) and all(0 <= s < len(spec.csg_states) for p in paths for s in p)
+    assert MO.build_parser().parse_args([]).max_force == -1 and MO.MAX_FORCE_DEFAULT == 80.0
