@@ -253,6 +253,27 @@ def test_model_optimize_driver_serial_and_batched(EN, tmp_path):
     assert [r["path"] for r in resv] == [[1, 2], [1, 7]] and all(np.isfinite(r["best"]) for r in resv)
 
 
+def test_model_test_recording_mirror(EN, tmp_path):
+    """model_test.py:115-135 without --add_physics: one replay, [N*50,7] object poses and [N*50,5,6] fingertip records."""
+    from synthesize_pregrasp_b200 import model_test as MT
+    g = recorded("foodbox_20.0")
+    raw = np.load(os.path.join(ROOT, "tests", "golden", "recorded_tip_records.npz"))["foodbox_20p0"]
+    os.makedirs(tmp_path / "traj")
+    np.save(tmp_path / "traj" / "foodbox_20.0.npy", g["u"])
+    MT.main(["--exp_name", "foodbox_20.0", "--env", "foodbox", "--data_dir", str(tmp_path)])
+    poses = np.load(tmp_path / "object_poses" / "foodbox_20.0_object_poses.npy")
+    tips = np.load(tmp_path / "tip_data" / "foodbox_20.0_tip_poses.npy")
+    assert poses.shape == (100, 7) and tips.shape == (100, 5, 6) and np.all(tips[:, 2:] == 100.0)
+    # the first substeps reproduce the PyBullet recording (the later ones as far as the oracle does, DESIGN.md section 2)
+    assert np.abs(poses[:6] - g["poses"][:6]).max() <= 1e-7
+    assert np.abs(tips[:6, :2] - raw[:6, :2]).max() <= 1e-6
+    # every row: the record is the object pose applied to the decoded local contact point
+    tips2, poses2, J, metric = MT.record("foodbox", g["u"], 20.0)
+    np.testing.assert_array_equal(poses2, poses)
+    np.testing.assert_array_equal(tips2, tips)
+    assert np.isfinite(J) and np.isfinite(metric)
+
+
 def test_errors_are_reported_not_swallowed(EN):
     from synthesize_pregrasp_b200.envspec import make_spec
     import dataclasses

@@ -281,3 +281,28 @@ def test_model_optimize_driver_arguments_and_paths():
     spec = make_spec("plate")
     assert len(paths) == min(10, len(spec.paths_id)) and all(0 <= s < len(spec.csg_states) for p in paths for s in p)
     assert MO.build_parser().parse_args([]).max_force == -1 and MO.MAX_FORCE_DEFAULT == 80.0
+
+
+@pytest.mark.parametrize("exp", ["plate_20.0", "foodbox_20.0", "waterbottle_20.0", "wall_laptop_20.0"])
+def test_tip_records_reproduce_recorded_tip_data(exp):
+    """model_test.py:115-135 recording format: object pose o local contact point + nearest-cloud-point normal for the two active
+    fingers, 100 for the three absent ones -- data/tip_data/<exp>_tip_poses.npy[:100] (tests/golden/recorded_tip_records.npz)."""
+    from synthesize_pregrasp_b200.model_test import tip_records
+    g = recorded(exp)
+    raw = np.load(os.path.join(ROOT, "tests", "golden", "recorded_tip_records.npz"))[exp.replace(".", "p")]
+    spec = make_spec(g["env"])
+    reg = oracle_regions(spec, spec.dummy_states)
+    carry = D.new_carry()
+    local, on = [], []
+    for j in range(2):
+        pos, o, _ = D.decode_step(g["u"][j], carry, reg, [0, 0, 0], j)
+        local.append(pos.copy()); on.append(o.copy())
+    got = tip_records(g["poses"], np.stack(local), spec.cloud, spec.cloud_normals)
+    assert got.shape == raw.shape == (100, 5, 6) and np.all(got[:, 2:] == 100.0) and np.all(raw[:, 2:] == 100.0)
+    for j in range(2):
+        rows = slice(50 * j, 50 * j + 50)
+        for f in range(2):
+            # a finger that is off sits at the local point (100,100,100): its world position carries the recording's float noise
+            assert np.abs(got[rows, f, :3] - raw[rows, f, :3]).max() <= (1e-7 if on[j][f] else 5e-5)
+            if on[j][f]:
+                assert np.abs(got[rows, f, 3:] - raw[rows, f, 3:]).max() <= 5e-7

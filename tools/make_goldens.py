@@ -151,6 +151,12 @@ def gen_recorded():
         out[k + "__env"] = np.array(env)
         out[k + "__max_force"] = np.float64(exp.split("_")[-1])
     np.savez_compressed(os.path.join(OUT, "recorded_trajectories.npz"), **out)
+    # full fingertip records (position + normal, all five slots) of the recordings whose normals the stored clouds reproduce:
+    # the target of synthesize_pregrasp_b200/model_test.py::tip_records
+    full = {}
+    for exp in ("plate_20.0", "foodbox_20.0", "waterbottle_20.0", "wall_laptop_20.0"):
+        full[exp.replace(".", "p")] = np.load(os.path.join(REF, f"data/tip_data/{exp}_tip_poses.npy"))[:100]
+    np.savez_compressed(os.path.join(OUT, "recorded_tip_records.npz"), **full)
 
 
 if __name__ == "__main__":
