@@ -180,7 +180,11 @@ struct Params {
   int manifold_order = 0;         // 0: emulate quickSort of dispatcher order; k>=1: (k-1)-th permutation of creation order
   int constraint_reverse = 1;     // [H] quickSort of equal island ids reverses the two servo constraints
   int residual_max = 1;           // 1: max over rows, 0: sum
-  int merge_islands = 1;          // [H] all islands go through ONE solver call (batching), global early-out
+  int merge_islands = 0;          // every island is its own solver call with its own early-out: PyBullet's server sets
+                                  // minimumSolverBatchSize = 0.  Decided by cardboard_20.0, where the two parked fingertips collide
+                                  // with each other: 1e-16 over 50 rows this way, 2e-7 growing to 1e-6 with one merged solve
+                                  // (which would iterate the object's island until the fingertips' island converges);
+                                  // every other recording is indifferent
   double default_max_impulse = 500.0;
   int pair_flip = 0;              // debugging: reverse the uid rule for non-compound pairs
   int force_iters = 0, force_step = 0;  // debugging: run exactly force_iters iterations at substep #force_step

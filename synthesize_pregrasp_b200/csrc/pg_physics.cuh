@@ -759,8 +759,15 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
   }
 
   rs.nc.n = 0; rs.n_pts = 0;
+  // Islands are solved one after the other, each with its own early exit (PyBullet's server sets minimumSolverBatchSize = 0,
+  // so btMultiBodyDynamicsWorld hands every island to the solver separately; the cardboard recording, whose two parked
+  // fingertips collide with each other far away, is reproduced to 1e-16 only this way).  Manifolds and constraints are sorted
+  // by island id, so the rows of island t are the contiguous ranges [p_lo[t], p_hi[t]) and [c_lo[t], c_hi[t]).
+  int p_lo[3] = {0, 0, 0}, p_hi[3] = {0, 0, 0}, c_lo[3] = {0, 0, 0}, c_hi[3] = {0, 0, 0};
   for (int o = 0; o < S.nman; o++) {
     const Manifold& m = S.man[mval[o]];
+    const int isl = mkey[o];
+    if (p_hi[isl] == p_lo[isl]) p_lo[isl] = rs.n_pts;
     BodyView A = view(E, S, statR, m.a), B = view(E, S, statR, m.b);
     double f = A.friction * B.friction;
     if (f < -10.0) f = -10.0;
@@ -779,8 +786,14 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
       contact_row_setup(E, S, sm, ss, m.a, m.b, r.relA, r.relB, r.l2, 0.0, true, r.inv2, r.den2, r.rhs2);
       r.impN = 0; r.imp1 = 0; r.imp2 = 0;
     }
+    p_hi[isl] = rs.n_pts;
   }
-  for (int c = 0; c < ncons; c++) setup_fixed_rows(E, S, sm, ss, cval[c], rs.nc);
+  for (int c = 0; c < ncons; c++) {
+    const int isl = ckey[c];
+    if (c_hi[isl] == c_lo[isl]) c_lo[isl] = rs.nc.n;
+    setup_fixed_rows(E, S, sm, ss, cval[c], rs.nc);
+    c_hi[isl] = rs.nc.n;
+  }
   S.last_iterations = 0;
 #if defined(PG_HOST_STATS) && !defined(__CUDA_ARCH__)
   { extern long g_stat_pts[32], g_stat_nc[16]; g_stat_pts[rs.n_pts < 31 ? rs.n_pts : 31]++; g_stat_nc[rs.nc.n < 15 ? rs.nc.n : 15]++; }
@@ -808,7 +821,6 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
 #else
 #define PG_AUDIT(slot, n)
 #endif
-  const int nn = rs.nc.n;
   const double mi0 = max_imp[0], mi1 = max_imp[1];
   const int ncb0 = rs.nc.body[0], ncb1 = rs.nc.body[1];
   auto load_nc = [&](int index) -> NcRegs {
@@ -829,16 +841,20 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
     return q;
   };
 
+  int it_max = 0;
+  for (int isl = 0; isl < 3; isl++) {
+  const int n0 = c_lo[isl], nn = c_hi[isl] - c_lo[isl], p0 = p_lo[isl], p1 = p_hi[isl];
+  if (nn == 0 && p1 == p0) continue;
   int it;
   for (it = 0; it < E.iterations; it++) {
     double lsr = 0;
     // ---- fingertip servo rows, alternating sweep direction
     if (nn > 0) {
-      NcRegs cur = load_nc((it & 1) ? 0 : nn - 1);
+      NcRegs cur = load_nc(n0 + ((it & 1) ? 0 : nn - 1));
       for (int j = 0; j < nn; j++) {
-        const int index = (it & 1) ? j : nn - 1 - j;
+        const int index = n0 + ((it & 1) ? j : nn - 1 - j);
         NcRegs nxt = cur;
-        if (j + 1 < nn) nxt = load_nc((it & 1) ? j + 1 : nn - 2 - j);
+        if (j + 1 < nn) nxt = load_nc(n0 + ((it & 1) ? j + 1 : nn - 2 - j));
         const int d = cur.d, i = cur.i;
         double delta = cur.rhs, imp = cur.imp;
         if (i < 3) {
@@ -862,11 +878,11 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
       }
     }
     // ---- normal rows
-    if (rs.n_pts > 0) {
-      NRegs cur = load_n(0);
-      for (int k = 0; k < rs.n_pts; k++) {
+    if (p1 > p0) {
+      NRegs cur = load_n(p0);
+      for (int k = p0; k < p1; k++) {
         NRegs nxt = cur;
-        if (k + 1 < rs.n_pts) nxt = load_n(k + 1);
+        if (k + 1 < p1) nxt = load_n(k + 1);
         const int da = cur.da, db = cur.db;
         V3 n = cur.n, tA = cross(cur.relA, n), tB = cross(cur.relB, -n);
         double delta = cur.rhs, a = 0, b = 0;
@@ -888,7 +904,7 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
       }
     }
     // ---- friction pairs with the implicit cone
-    for (int k = 0; k < rs.n_pts; k++) {
+    for (int k = p0; k < p1; k++) {
       PRow& r = rs.pt[k];
       // no normal impulse and no stored friction impulse: the cone clips both rows to zero, nothing changes
       // (identical result, zero residual) -- skip the row pair
@@ -930,7 +946,9 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
     PG_AUDIT(3, 1);                                       // iterations
     if (lsr <= E.residual_threshold || it >= E.iterations - 1) { it++; break; }
   }
-  S.last_iterations = it;
+  if (it > it_max) it_max = it;
+  }
+  S.last_iterations = it_max;
   for (int d = 0; d < 3; d++) {
     DynBody& b = S.dyn[d];
     V3 w = sm_w(sm, ss, d), v = sm_v(sm, ss, d);

@@ -99,7 +99,8 @@ def test_cost_geometry_against_brute_force():
 
 PHYS = {  # exp: (rows to check, tolerance on pose) -- achieved tolerances, see DESIGN.md "Oracle / physics"
     "foodbox_20.0": (range(0, 11), 1e-7), "keyboard_20.0": (range(0, 31), 1e-7), "keyboard_scale_20.0": (range(0, 50), 2e-7),
-    "wall_laptop_20.0": (range(0, 6), 1e-9), "cardboard_20.0": (range(0, 50), 2e-6),
+    "wall_laptop_20.0": (range(0, 6), 1e-9),
+    "cardboard_20.0": (range(0, 51), 1e-12),  # both fingertips parked (and colliding with each other): per-island solves, exact over env step 1
     "plate_20.0": (range(0, 37), 1e-8),      # hull object: GJK + EPA narrowphase, compound pair rules
     "waterbottle_20.0": (range(0, 3), 1e-9),  # URDF cylinder = 64-vertex prism hull; later rows: manifold order of the
                                               # late floor contact is not recovered
@@ -117,7 +118,7 @@ def test_physics_oracle_against_recorded_trajectories(exp):
     P = np.concatenate([sim.step(g["u"][j], [0, 0, 0])["poses"] for j in range(2)])
     rows, tol = PHYS[exp]
     err = np.minimum(np.abs(P - g["poses"]), np.abs(P * np.r_[1, 1, 1, -1, -1, -1, -1] - g["poses"]))   # q and -q are one rotation
-    assert err[0].max() <= (1e-12 if exp != "cardboard_20.0" else 2e-7)      # reset + pre-simulate substeps: exact
+    assert err[0].max() <= 1e-12      # reset + pre-simulate substeps: exact
     assert err[list(rows)].max() <= tol, err[list(rows)].max(axis=1)
     # whole 100-substep horizon stays physically close (contact-rich motion is chaotic)
     assert err[:, :3].max() <= 5e-2
