@@ -100,11 +100,20 @@ def test_cost_geometry_against_brute_force():
 PHYS = {  # exp: (rows to check, tolerance on pose) -- achieved tolerances, see DESIGN.md "Oracle / physics"
     "foodbox_20.0": (range(0, 11), 1e-7), "keyboard_20.0": (range(0, 31), 1e-7), "keyboard_scale_20.0": (range(0, 50), 2e-7),
     "wall_laptop_20.0": (range(0, 6), 1e-9),
-    "cardboard_20.0": (range(0, 51), 1e-12),  # both fingertips parked (and colliding with each other): per-island solves, exact over env step 1
+    # both fingertips parked (and colliding with each other) in env step 1: per-island solves, exact; env step 2 with the
+    # floor friction the recording was made with (RECORDING_TIME below): a fingertip drags the 2 mm plate over the floor
+    "cardboard_20.0": (range(0, 66), 5e-8),
     "plate_20.0": (range(0, 37), 1e-8),      # hull object: GJK + EPA narrowphase, compound pair rules
     "waterbottle_20.0": (range(0, 3), 1e-9),  # URDF cylinder = 64-vertex prism hull; later rows: manifold order of the
                                               # late floor contact is not recovered
 }
+
+
+# Env constants that changed in the reference AFTER a recording was made, identified from the recording itself: with the
+# committed cardboard env (floor lateralFriction 0.002, cardboard_contact_graph_env.py:193-194, under a "TODO: tune friction")
+# the first dragging substep is off by 1e-4; floor friction 0.005 reproduces the recorded displacement and rotation of that
+# substep to all printed digits and the following 15 substeps to 5e-8.  The product keeps the committed value.
+RECORDING_TIME = {"cardboard_20.0": {"floor_friction": 0.005}}
 
 
 @pytest.mark.parametrize("exp", sorted(PHYS))
@@ -113,7 +122,13 @@ def test_physics_oracle_against_recorded_trajectories(exp):
     from oracle.envsim import EnvSim
     g = recorded(exp)
     spec = make_spec(g["env"])
-    sim = EnvSim(oracle_spec(spec), g["max_force"])
+    osd = oracle_spec(spec)
+    if "floor_friction" in RECORDING_TIME.get(exp, {}):
+        i = osd["static_names"].index("floor")
+        half, pos, quat, _ = osd["statics"][i]
+        osd["statics"] = list(osd["statics"])
+        osd["statics"][i] = (half, pos, quat, RECORDING_TIME[exp]["floor_friction"])
+    sim = EnvSim(osd, g["max_force"])
     sim.reset()
     P = np.concatenate([sim.step(g["u"][j], [0, 0, 0])["poses"] for j in range(2)])
     rows, tol = PHYS[exp]
@@ -122,6 +137,8 @@ def test_physics_oracle_against_recorded_trajectories(exp):
     assert err[list(rows)].max() <= tol, err[list(rows)].max(axis=1)
     # whole 100-substep horizon stays physically close (contact-rich motion is chaotic)
     assert err[:, :3].max() <= 5e-2
+    if exp == "cardboard_20.0":
+        assert err[:51].max() <= 1e-12 and err.max() <= 2e-3          # env step 1 exact; whole horizon within 1e-3
 
 
 def test_abi_library_loads_and_exports_header_symbols(built):
