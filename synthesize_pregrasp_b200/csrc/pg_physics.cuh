@@ -445,13 +445,16 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
   }
   // New manifolds are created in broadphase pair-cache order.  After PyBullet's setCollisionFilterPair sequence
   // (every call re-creates both proxies) the cache holds: the surviving tip-tip and wall-tip pairs, then what the
-  // re-created object proxy found at creation -- dynamic tree (index tip, thumb; only tips whose tight AABB
-  // overlapped the object's), then the static tree -- then the tip pairs found with fat AABBs (DESIGN.md "Row order").
+  // re-created object proxy found at creation -- the first wall, the dynamic tree (index tip, thumb; only tips whose tight
+  // AABB overlapped the object's), then the rest of the static tree -- then the tip pairs found with fat AABBs (DESIGN.md "Row order").
   int ca[MAXM + 6], cb[MAXM + 6], nc = 0;
   bool tt_early = true;
   for (int k = 0; k < 3; k++) if (S.plo[0][k] > S.phi[1][k] || S.phi[0][k] < S.plo[1][k]) tt_early = false;
   if (tt_early) { ca[nc] = B_TIP0; cb[nc++] = B_TIP1; }
   for (int s = 0; s < E.n_static; s++) if (!E.statics[s].compound) { ca[nc] = s; cb[nc++] = B_TIP1; ca[nc] = s; cb[nc++] = B_TIP0; }
+  // the first wall's pair with the object precedes the early fingertip pairs (waterbottle recording: the floor's child manifold,
+  // created mid-run, is then solved after the fingertip's; laptop recording improves as well, the others are indifferent)
+  for (int s = 0; s < E.n_static; s++) if (!E.statics[s].compound) { ca[nc] = s; cb[nc++] = B_OBJ; break; }
   for (int t = 1; t >= 0; t--) if ((S.early >> t) & 1u) { ca[nc] = B_OBJ; cb[nc++] = B_TIP0 + t; }
   for (int s = 0; s < E.n_static; s++) if (E.statics[s].compound) { ca[nc] = s; cb[nc++] = B_OBJ; }
   for (int s = 0; s < E.n_static; s++) if (!E.statics[s].compound) { ca[nc] = s; cb[nc++] = B_OBJ; }

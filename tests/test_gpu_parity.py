@@ -53,7 +53,7 @@ def test_physics_kernel_random_batch(EN, env, F):
     from synthesize_pregrasp_b200.envspec import make_spec
     spec = make_spec(env)
     eng = EN.RolloutEngine(spec, device=0)
-    K, N = 24, 2
+    K, N = 48, 2
     gen = torch.Generator(device="cuda:0").manual_seed(1234)
     noise = 0.8 * torch.randn((K, N, 48), generator=gen, device="cuda:0", dtype=torch.float32)
     u = np.zeros((N, 48))
@@ -73,8 +73,10 @@ def test_physics_kernel_random_batch(EN, env, F):
     # contact-rich rollouts are chaotic: a rounding-level difference can flip a contact event late in the
     # 200-400 substeps; require the bulk to agree within 1e-4 and report the fraction
     print(f"{env}: {ok}/{K} rollouts within 1e-4 of the oracle at both cost instants")
-    # the toppling bottle (403 substeps, polytope contacts) is the most chaotic env: 79 % measured, 60 % required
-    assert ok >= int((0.6 if env == "waterbottle" else 0.75) * K), ok
+    # measured agreement (160 rollouts on the GPU, 96 with the host build of the kernel code): 85-99 %, the toppling bottle
+    # (403 substeps, polytope contacts) 73-79 %; required of these 48: 70 % and 55 %, so that the sample's own scatter
+    # (binomial, sd ~2.5 rollouts) cannot fail the test
+    assert ok >= int((0.55 if env == "waterbottle" else 0.70) * K), ok
 
 
 @pytest.mark.parametrize("env", ["plate", "waterbottle", "foodbox", "bookshelf", "keyboard", "laptop", "cardboard"])

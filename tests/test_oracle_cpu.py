@@ -104,8 +104,9 @@ PHYS = {  # exp: (rows to check, tolerance on pose) -- achieved tolerances, see 
     # floor friction the recording was made with (RECORDING_TIME below): a fingertip drags the 2 mm plate over the floor
     "cardboard_20.0": (range(0, 66), 5e-8),
     "plate_20.0": (range(0, 37), 1e-8),      # hull object: GJK + EPA narrowphase, compound pair rules
-    "waterbottle_20.0": (range(0, 3), 1e-9),  # URDF cylinder = 64-vertex prism hull; later rows: manifold order of the
-                                              # late floor contact is not recovered
+    # URDF cylinder = 64-vertex prism hull; rows 3+: the floor's child manifold is created mid-run and must be solved after the
+    # fingertip's, which the pair-cache order delivers once the first (object, wall) pair precedes the fingertip pairs
+    "waterbottle_20.0": (range(0, 37), 5e-6),
 }
 
 
@@ -137,6 +138,8 @@ def test_physics_oracle_against_recorded_trajectories(exp):
     assert err[list(rows)].max() <= tol, err[list(rows)].max(axis=1)
     # whole 100-substep horizon stays physically close (contact-rich motion is chaotic)
     assert err[:, :3].max() <= 5e-2
+    if exp == "waterbottle_20.0":
+        assert err[:18].max() <= 1e-8
     if exp == "cardboard_20.0":
         assert err[:51].max() <= 1e-12 and err.max() <= 2e-3          # env step 1 exact; whole horizon within 1e-3
 
