@@ -63,6 +63,33 @@ def qmat(q):
                      [xz - wy, yz + wx, 1.0 - (xx + yy)]])
 
 
+def b3_multiply_transforms(posA, ornA, posB):
+    """pybullet.multiplyTransforms(posA, ornA, posB, [0,0,0,1])[0] as PyBullet computes it: b3Transform with b3Scalar = FLOAT
+    (PhysicsClientC_API.cpp b3MultiplyTransforms; the extension is built with double-precision Bullet but single-precision
+    Bullet3Common).  Pinned by data/tip_data/*: this reproduces the recorded fingertip positions bit for bit (every row of the
+    foodbox, keyboard, laptop, waterbottle and cardboard recordings), the double-precision product only to 1e-8.  The env feeds
+    these float32 results into the physics: teleport position / constraint pivot (plate_env:462-474) and servo targets (:526-530)."""
+    f = np.float32
+    x, y, z, w = (f(v) for v in ornA)
+    d = f(f(f(f(x * x) + f(y * y)) + f(z * z)) + f(w * w))            # b3Quaternion::length2 = dot(q, q)
+    s = f(f(2.0) / d)                                                 # b3Matrix3x3::setRotation
+    xs, ys, zs = f(x * s), f(y * s), f(z * s)
+    wx, wy, wz = f(w * xs), f(w * ys), f(w * zs)
+    xx, xy, xz = f(x * xs), f(x * ys), f(x * zs)
+    yy, yz, zz = f(y * ys), f(y * zs), f(z * zs)
+    one = f(1.0)
+    R = ((f(one - f(yy + zz)), f(xy - wz), f(xz + wy)),
+         (f(xy + wz), f(one - f(xx + zz)), f(yz - wx)),
+         (f(xz - wy), f(yz + wx), f(one - f(xx + yy))))
+    v = [f(t) for t in posB]
+    o = [f(t) for t in posA]
+    out = np.empty(3)
+    for i in range(3):                                                # b3Transform::operator(): dot3 (left to right) + origin
+        acc = f(f(f(v[0] * R[i][0]) + f(v[1] * R[i][1])) + f(v[2] * R[i][2]))
+        out[i] = f(acc + o[i])
+    return out
+
+
 class EnvSim:
     """spec keys: obj_shape, obj_half, obj_hull, obj_mass, obj_pos, obj_quat, obj_friction,
     statics=[(half,pos,quat,friction)], order=[names], static_names, tip_half=[thumb, other], tip_friction,
@@ -72,6 +99,7 @@ class EnvSim:
         self.s = spec
         self.max_force = float(max_force)
         self.params = dict(params or {})
+        self.f32_api = bool(self.params.pop("f32_api", 1))         # pybullet.multiplyTransforms in float32 (see b3_multiply_transforms)
         self.h = None
         self.L = lib()
 
@@ -169,7 +197,7 @@ class EnvSim:
             for i in range(2):
                 L.pgo_remove_constraint(h, i)
         for i in range(2):
-            g = pos + R @ cur_pos[i]
+            g = b3_multiply_transforms(pos, quat, cur_pos[i]) if self.f32_api else pos + R @ cur_pos[i]
             if not self._clear(g):
                 g = np.array([100.0, 100.0, 100.0])
             L.pgo_set_filter(h, self.tips[i], self.obj, 0)
@@ -191,8 +219,12 @@ class EnvSim:
             R = qmat(quat)
             vel = self.vel(self.obj)[:3]
             for i in range(2):
-                v_g = R @ f_interp[i][:, t] + vel * D.DT
-                tar = (pos + R @ cur_pos[i]) + v_g
+                if self.f32_api:
+                    v_g = b3_multiply_transforms(np.zeros(3), quat, f_interp[i][:, t]) + vel * D.DT
+                    tar = b3_multiply_transforms(pos, quat, cur_pos[i]) + v_g
+                else:
+                    v_g = R @ f_interp[i][:, t] + vel * D.DT
+                    tar = (pos + R @ cur_pos[i]) + v_g
                 a1, tp = _p(tar)
                 a2, qp = _p(quat)
                 L.pgo_change_constraint(h, i, tp, qp, self.max_force)

@@ -42,6 +42,42 @@ PG_HD Q4 qmul(Q4 a, Q4 b) {
   r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
   return r;
 }
+
+// pybullet.multiplyTransforms(posA, ornA, posB, identity)[0] exactly as PyBullet computes it: b3Transform with b3Scalar = FLOAT
+// (b3MultiplyTransforms; the extension has double-precision Bullet but single-precision Bullet3Common).  The env feeds these
+// float32 results into the physics -- fingertip teleport position / constraint pivot (plate_env:462-474) and the servo targets
+// (:526-530) -- and the recorded fingertip positions are reproduced bit for bit only this way.  Every operation is a single
+// IEEE float operation in b3's order (no contraction: intrinsics on the device, -ffp-contract=off in the host test build).
+#if defined(__CUDA_ARCH__)
+#define PG_FMUL(a, b) __fmul_rn((a), (b))
+#define PG_FADD(a, b) __fadd_rn((a), (b))
+#define PG_FSUB(a, b) __fsub_rn((a), (b))
+#define PG_FDIV(a, b) __fdiv_rn((a), (b))
+#else
+#define PG_FMUL(a, b) ((float)((float)(a) * (float)(b)))
+#define PG_FADD(a, b) ((float)((float)(a) + (float)(b)))
+#define PG_FSUB(a, b) ((float)((float)(a) - (float)(b)))
+#define PG_FDIV(a, b) ((float)((float)(a) / (float)(b)))
+#endif
+PG_HD V3 b3_multiply_transforms(V3 posA, Q4 ornA, V3 posB) {
+  const float x = (float)ornA.x, y = (float)ornA.y, z = (float)ornA.z, w = (float)ornA.w;
+  const float d = PG_FADD(PG_FADD(PG_FADD(PG_FMUL(x, x), PG_FMUL(y, y)), PG_FMUL(z, z)), PG_FMUL(w, w));   // b3Quaternion::length2
+  const float s = PG_FDIV(2.0f, d);                                                                         // b3Matrix3x3::setRotation
+  const float xs = PG_FMUL(x, s), ys = PG_FMUL(y, s), zs = PG_FMUL(z, s);
+  const float wx = PG_FMUL(w, xs), wy = PG_FMUL(w, ys), wz = PG_FMUL(w, zs);
+  const float xx = PG_FMUL(x, xs), xy = PG_FMUL(x, ys), xz = PG_FMUL(x, zs);
+  const float yy = PG_FMUL(y, ys), yz = PG_FMUL(y, zs), zz = PG_FMUL(z, zs);
+  const float r00 = PG_FSUB(1.0f, PG_FADD(yy, zz)), r01 = PG_FSUB(xy, wz), r02 = PG_FADD(xz, wy);
+  const float r10 = PG_FADD(xy, wz), r11 = PG_FSUB(1.0f, PG_FADD(xx, zz)), r12 = PG_FSUB(yz, wx);
+  const float r20 = PG_FSUB(xz, wy), r21 = PG_FADD(yz, wx), r22 = PG_FSUB(1.0f, PG_FADD(xx, yy));
+  const float v0 = (float)posB.x, v1 = (float)posB.y, v2 = (float)posB.z;
+  // b3Transform::operator(): dot3 (products summed left to right) + origin
+  const float o0 = PG_FADD(PG_FADD(PG_FADD(PG_FMUL(v0, r00), PG_FMUL(v1, r01)), PG_FMUL(v2, r02)), (float)posA.x);
+  const float o1 = PG_FADD(PG_FADD(PG_FADD(PG_FMUL(v0, r10), PG_FMUL(v1, r11)), PG_FMUL(v2, r12)), (float)posA.y);
+  const float o2 = PG_FADD(PG_FADD(PG_FADD(PG_FMUL(v0, r20), PG_FMUL(v1, r21)), PG_FMUL(v2, r22)), (float)posA.z);
+  return V3((double)o0, (double)o1, (double)o2);
+}
+
 PG_HD Q4 qnormalize(Q4 q) {
   double l = sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
   Q4 r; r.x = q.x / l; r.y = q.y / l; r.z = q.z / l; r.w = q.w / l;

@@ -235,7 +235,7 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
       DynBody& o = S.dyn[0];
       M3 R = qmat(o.q);
       for (int i = 0; i < NFING; i++) {
-        V3 g = o.pos + mul(R, cur_pos[i]);
+        V3 g = b3_multiply_transforms(o.pos, o.q, cur_pos[i]);       // float32, as pybullet.multiplyTransforms returns it
         if (!check_clearance(E, g)) g = V3(100.0, 100.0, 100.0);
         S.filter_off |= (1u << i);
         refresh_proxy<SHAPE>(E, S, B_TIP0 + i);
@@ -263,8 +263,8 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
       V3 vel = o.v;
       for (int i = 0; i < NFING; i++) {
         V3 f(interp7(E, &knots[i][0][0], 3, t), interp7(E, &knots[i][0][1], 3, t), interp7(E, &knots[i][0][2], 3, t));
-        V3 v_g = mul(R, f) + vel * E.dt;
-        V3 tar = (o.pos + mul(R, cur_pos[i])) + v_g;
+        V3 v_g = b3_multiply_transforms(V3(), o.q, f) + vel * E.dt;       // the two transforms in float32 (pg_math.cuh), the sums in double
+        V3 tar = b3_multiply_transforms(o.pos, o.q, cur_pos[i]) + v_g;
         S.cons[i].pivotB = tar; S.cons[i].frameB = R; S.cons[i].max_impulse = max_force * E.dt;
       }
       substep<SHAPE>(E, S, statR, rs, sm, ss);

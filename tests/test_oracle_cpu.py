@@ -98,8 +98,10 @@ def test_cost_geometry_against_brute_force():
 
 
 PHYS = {  # exp: (rows to check, tolerance on pose) -- achieved tolerances, see DESIGN.md "Oracle / physics"
-    "foodbox_20.0": (range(0, 11), 1e-7), "keyboard_20.0": (range(0, 31), 1e-7), "keyboard_scale_20.0": (range(0, 50), 2e-7),
-    "wall_laptop_20.0": (range(0, 6), 1e-9),
+    # With pybullet.multiplyTransforms emulated in float32 (oracle/envsim.py b3_multiply_transforms) the agreement is at rounding
+    # level up to the first discrete contact event the restatement does not reproduce (foodbox row 12, laptop row 7, keyboard 37)
+    "foodbox_20.0": (range(0, 12), 1e-12), "keyboard_20.0": (range(0, 24), 1e-12), "keyboard_scale_20.0": (range(0, 50), 2e-7),
+    "wall_laptop_20.0": (range(0, 7), 1e-12),
     # both fingertips parked (and colliding with each other) in env step 1: per-island solves, exact; env step 2 with the
     # floor friction the recording was made with (RECORDING_TIME below): a fingertip drags the 2 mm plate over the floor
     "cardboard_20.0": (range(0, 66), 5e-8),
@@ -140,6 +142,10 @@ def test_physics_oracle_against_recorded_trajectories(exp):
     assert err[:, :3].max() <= 5e-2
     if exp == "waterbottle_20.0":
         assert err[:18].max() <= 1e-8
+    if exp == "keyboard_20.0":
+        assert err[:37].max() <= 1e-10
+    if exp == "plate_20.0":
+        assert err[:7].max() <= 1e-10
     if exp == "cardboard_20.0":
         assert err[:51].max() <= 1e-12 and err.max() <= 2e-3          # env step 1 exact; whole horizon within 1e-3
 
