@@ -5,7 +5,8 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 legs use it, as the checker or the CPU baseline, never as the thing shipped.
 
 Parity status of each piece (see DESIGN.md "Oracle"):
-  decode.py    pinned: reproduces the reference's recorded tip positions (data/tip_data) <= 2e-8
+  decode.py    pinned: reproduces the reference's recorded tip positions (data/tip_data) bit for bit (box envs; plate
+               <= 1 float32 ulp) through the single-precision pybullet.multiplyTransforms restated in envsim.py
   scorenet.py  pinned: equals the reference's neurals/network.py LargeScoreFunction run on CPU
   cost.py      pinned against brute-force definitions (Open3D itself is not installable here)
   mppi.py      pinned: same numbers as stoch_traj_opt.py:195-204 run in this container

@@ -28,10 +28,30 @@ from . import envspec as ES
 NUM_TIP_SLOTS = 5                    # model_test.py:29
 
 
-def _qrot(q, v):
-    x, y, z, w = q
-    u = np.array([x, y, z])
-    return v + 2.0 * np.cross(u, np.cross(u, v) + w * v)
+def multiply_transforms(posA, ornA, posB):
+    """pybullet.multiplyTransforms(posA, ornA, posB, [0,0,0,1])[0] as PyBullet computes it: in SINGLE precision (b3Transform with
+    b3Scalar = float), every operation a float32 operation in b3's order.  The reference's recorded fingertip files hold exactly
+    these float32 values (reproduced bit for bit from the recorded poses by tests/test_oracle_cpu.py); the rollout kernel computes
+    its servo targets the same way (csrc/pg_math.cuh b3_multiply_transforms)."""
+    f = np.float32
+    x, y, z, w = (f(v) for v in ornA)
+    d = f(f(f(f(x * x) + f(y * y)) + f(z * z)) + f(w * w))
+    s = f(f(2.0) / d)
+    xs, ys, zs = f(x * s), f(y * s), f(z * s)
+    wx, wy, wz = f(w * xs), f(w * ys), f(w * zs)
+    xx, xy, xz = f(x * xs), f(x * ys), f(x * zs)
+    yy, yz, zz = f(y * ys), f(y * zs), f(z * zs)
+    one = f(1.0)
+    R = ((f(one - f(yy + zz)), f(xy - wz), f(xz + wy)),
+         (f(xy + wz), f(one - f(xx + zz)), f(yz - wx)),
+         (f(xz - wy), f(yz + wx), f(one - f(xx + yy))))
+    v = [f(t) for t in posB]
+    o = [f(t) for t in posA]
+    out = np.empty(3)
+    for i in range(3):
+        acc = f(f(f(v[0] * R[i][0]) + f(v[1] * R[i][1])) + f(v[2] * R[i][2]))
+        out[i] = f(acc + o[i])
+    return out
 
 
 def tip_records(object_poses, local_points, cloud, cloud_normals, control_skip=ES.CONTROL_SKIP):
@@ -50,8 +70,8 @@ def tip_records(object_poses, local_points, cloud, cloud_normals, control_skip=E
                 break
             pos, quat = object_poses[row, :3], object_poses[row, 3:]
             for f in range(F):
-                out[row, f, :3] = _qrot(quat, local_points[j, f]) + pos
-                out[row, f, 3:] = _qrot(quat, cloud_normals[nn[f]])
+                out[row, f, :3] = multiply_transforms(pos, quat, local_points[j, f])              # plate_env:515
+                out[row, f, 3:] = multiply_transforms(np.zeros(3), quat, cloud_normals[nn[f]])    # plate_env:518
     return out
 
 
