@@ -187,6 +187,7 @@ struct Params {
                                   // every other recording is indifferent
   double default_max_impulse = 500.0;
   int pair_flip = 0;              // debugging: reverse the uid rule for non-compound pairs
+  int dbg_step = 0, dbg_idx = -1; // debugging: force the cache slot of contacts added at one step
   int walls_first = 1;            // [H] this many (object, wall) pairs enter the pair cache before the early fingertip pairs: 1 (or 2)
                                   // carries waterbottle_20.0 from row 2 to row 20 (7e-8) and improves wall_laptop_20.0; 0 and 3 do not
   int force_iters = 0, force_step = 0;  // debugging: run exactly force_iters iterations at substep #force_step
@@ -324,6 +325,11 @@ static void add_contact(ContactSink& s, V3 normalOnB, V3 pointOnB, double depth)
   np.friction = f;
   plane_space1(np.normalB, np.lat1, np.lat2);
   int idx = manifold_cache_entry(m, np);
+  if (s.w->P.dbg_step > 0 && s.w->step_count == s.w->P.dbg_step && m.n == 4 &&
+      (m.a == s.w->tip[0] || m.a == s.w->tip[1] || m.b == s.w->tip[0] || m.b == s.w->tip[1])) {     // debugging: what-if on one insertion
+    if (s.w->P.dbg_idx == 9) return;
+    if (s.w->P.dbg_idx >= 0) { if (s.w->P.debug) fprintf(stderr, "dbg: natural idx %d -> %d\n", idx, s.w->P.dbg_idx); idx = s.w->P.dbg_idx; }
+  }
   if (idx >= 0) {
     np.impN = m.p[idx].impN; np.impL1 = m.p[idx].impL1; np.impL2 = m.p[idx].impL2; np.life = m.p[idx].life;
     m.p[idx] = np;
@@ -451,9 +457,11 @@ static void cull_points2(int n, double p[], int m, int i0, int iret[]) {
 }
 
 static int g_last_code = 0, g_last_cnum = 0;
+static double g_bb_fudge = 1.05;   // debugging: dBoxBox2's edge-axis preference factor
+static const bool g_bb_debug = getenv("PGO_BB_DEBUG") != nullptr;   // debugging: print every separating-axis value
 static int box_box(V3 p1, const M3& R1, V3 half1, V3 p2, const M3& R2, V3 half2, ContactSink& out) {
   g_last_code = 0; g_last_cnum = 0;
-  const double fudge_factor = 1.05;
+  const double fudge_factor = g_bb_fudge;
   V3 p, pp, normalC;
   int normalR_box = 0, normalR_col = -1;  // column of R1 (box 1) or R2 (box 2)
   double A[3], B[3], R[3][3], Q[3][3], s, s2, l;
@@ -466,6 +474,7 @@ static int box_box(V3 p1, const M3& R1, V3 half1, V3 p2, const M3& R2, V3 half2,
   s = -INFINITY; invert_normal = 0; code = 0;
 #define TST1(expr1, expr2, box, col, cc) \
   { double e1 = (expr1); s2 = std::fabs(e1) - (expr2); if (s2 > 0) return 0; \
+    if (g_bb_debug) fprintf(stderr, "    bb face %d s2 %.12e\n", (cc), s2); \
     if (s2 > s) { s = s2; normalR_box = box; normalR_col = col; invert_normal = (e1 < 0); code = (cc); } }
   TST1(pp[0], (A[0] + B[0] * Q[0][0] + B[1] * Q[0][1] + B[2] * Q[0][2]), 1, 0, 1);
   TST1(pp[1], (A[1] + B[0] * Q[1][0] + B[1] * Q[1][1] + B[2] * Q[1][2]), 1, 1, 2);
@@ -477,7 +486,7 @@ static int box_box(V3 p1, const M3& R1, V3 half1, V3 p2, const M3& R2, V3 half2,
 #define TST2(expr1, expr2, n1, n2, n3, cc) \
   { double e1 = (expr1); s2 = std::fabs(e1) - (expr2); if (s2 > kEps) return 0; \
     l = std::sqrt((n1) * (n1) + (n2) * (n2) + (n3) * (n3)); \
-    if (l > kEps) { s2 /= l; if (s2 * fudge_factor > s) { s = s2; normalR_col = -1; \
+    if (l > kEps) { s2 /= l; if (g_bb_debug) fprintf(stderr, "    bb edge %d s2 %.12e (x1.05 %.12e)\n", (cc), s2, s2 * fudge_factor); if (s2 * fudge_factor > s) { s = s2; normalR_col = -1; \
       normalC = V3((n1) / l, (n2) / l, (n3) / l); invert_normal = (e1 < 0); code = (cc); } } }
   const double fudge2 = (double)1.0e-5f;
   for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) Q[i][j] += fudge2;
@@ -493,6 +502,7 @@ static int box_box(V3 p1, const M3& R1, V3 half1, V3 p2, const M3& R2, V3 half2,
 #undef TST2
   if (!code) return 0;
   g_last_code = code;
+  if (g_bb_debug) fprintf(stderr, "    bb: code %d s %.12e normalC %.6f %.6f %.6f\n", code, s, normalC.x, normalC.y, normalC.z);
   V3 normal;
   if (normalR_col >= 0) normal = (normalR_box == 1 ? R1 : R2).col(normalR_col);
   else normal = mul(R1, normalC);
@@ -1144,12 +1154,13 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(walls_first) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }
   if (!strcmp(name, "hull_inertia_pad")) { g_hull_inertia_pad = v; return; }
   if (!strcmp(name, "pen_tie")) { g_pen_tie = v; return; }
+  if (!strcmp(name, "bb_fudge")) { g_bb_fudge = v; return; }
   if (!strcmp(name, "epa_variant")) { epa2::g_epa_variant = (int)v; return; }
   fprintf(stderr, "pgo_set_param: unknown %s\n", name);
 }
