@@ -188,6 +188,7 @@ struct Params {
   double default_max_impulse = 500.0;
   int pair_flip = 0;              // debugging: reverse the uid rule for non-compound pairs
   int pos_variant = 0;            // debugging: alternative right-hand sides for contacts with positive distance
+  int dbg_skip_new = 0;           // debugging: no new compound-child manifold at this step
   int dbg_step = 0, dbg_idx = -1; // debugging: force the cache slot of contacts added at one step
   int walls_first = 1;            // [H] this many (object, wall) pairs enter the pair cache before the early fingertip pairs: 1 (or 2)
                                   // carries waterbottle_20.0 from row 2 to row 20 (7e-8) and improves wall_laptop_20.0; 0 and 3 do not
@@ -763,6 +764,7 @@ static void collide(World& w) {
     if (filter_disabled(w, i, j)) continue;
     if (!pair_overlap(w, bi, bj)) continue;
     if (find_manifold(w, i, j)) continue;
+    if (w.P.dbg_skip_new > 0 && w.step_count == w.P.dbg_skip_new && (bi.compound || bj.compound)) continue;   // debugging what-if
     Manifold m;
     if (bi.compound) { m.a = i; m.b = j; }
     else if (bj.compound) { m.a = j; m.b = i; }
@@ -1160,7 +1162,7 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(pos_variant) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }
