@@ -38,6 +38,8 @@ def lib():
         L.pgo_create_constraint.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, dp, dp]
         L.pgo_change_constraint.argtypes = [ctypes.c_void_p, ctypes.c_int, dp, dp, ctypes.c_double]
         L.pgo_remove_constraint.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.pgo_b3_multiply_transforms.argtypes = [dp, dp, dp, dp]
+        L.pgo_b3_multiply_transforms.restype = None
         L.pgo_step.argtypes = [ctypes.c_void_p]
         L.pgo_last_iterations.argtypes = [ctypes.c_void_p]
         L.pgo_dump_manifolds.argtypes = [ctypes.c_void_p, dp, ctypes.c_int]
@@ -61,6 +63,16 @@ def qmat(q):
     yy, yz, zz = y * ys, y * zs, z * zs
     return np.array([[1.0 - (yy + zz), xy - wz, xz + wy], [xy + wz, 1.0 - (xx + zz), yz - wx],
                      [xz - wy, yz + wx, 1.0 - (xx + yy)]])
+
+
+def b3_multiply_transforms_native(lib, posA, ornA, posB):
+    """The same arithmetic through the C++ oracle library (oracle/physics pgo_b3_multiply_transforms): used inside EnvSim so that
+    the float32 emulation does not slow the CPU baseline down (the numpy version costs 40 % of a rollout)."""
+    a = np.ascontiguousarray(posA, np.float64); q = np.ascontiguousarray(ornA, np.float64); b = np.ascontiguousarray(posB, np.float64)
+    out = np.empty(3)
+    P = ctypes.POINTER(ctypes.c_double)
+    lib.pgo_b3_multiply_transforms(a.ctypes.data_as(P), q.ctypes.data_as(P), b.ctypes.data_as(P), out.ctypes.data_as(P))
+    return out
 
 
 def b3_multiply_transforms(posA, ornA, posB):
@@ -88,6 +100,9 @@ def b3_multiply_transforms(posA, ornA, posB):
         acc = f(f(f(v[0] * R[i][0]) + f(v[1] * R[i][1])) + f(v[2] * R[i][2]))
         out[i] = f(acc + o[i])
     return out
+
+
+_ZERO3 = np.zeros(3)
 
 
 class EnvSim:
@@ -197,7 +212,7 @@ class EnvSim:
             for i in range(2):
                 L.pgo_remove_constraint(h, i)
         for i in range(2):
-            g = b3_multiply_transforms(pos, quat, cur_pos[i]) if self.f32_api else pos + R @ cur_pos[i]
+            g = b3_multiply_transforms_native(L, pos, quat, cur_pos[i]) if self.f32_api else pos + R @ cur_pos[i]
             if not self._clear(g):
                 g = np.array([100.0, 100.0, 100.0])
             L.pgo_set_filter(h, self.tips[i], self.obj, 0)
@@ -218,10 +233,18 @@ class EnvSim:
             pos, quat = o[:3], o[3:]
             R = qmat(quat)
             vel = self.vel(self.obj)[:3]
+            if self.f32_api:                                   # both fingers in one native call (pgo_servo_targets)
+                DP = ctypes.POINTER(ctypes.c_double)
+                f6 = np.ascontiguousarray(np.stack([f_interp[0][:, t], f_interp[1][:, t]]))
+                c6 = np.ascontiguousarray(cur_pos, np.float64)
+                v3 = np.ascontiguousarray(vel)
+                o7 = np.ascontiguousarray(o)
+                tars = np.empty((2, 3))
+                L.pgo_servo_targets(o7.ctypes.data_as(DP), c6.ctypes.data_as(DP), f6.ctypes.data_as(DP), v3.ctypes.data_as(DP),
+                                    ctypes.c_double(float(D.DT)), tars.ctypes.data_as(DP))
             for i in range(2):
                 if self.f32_api:
-                    v_g = b3_multiply_transforms(np.zeros(3), quat, f_interp[i][:, t]) + vel * D.DT
-                    tar = b3_multiply_transforms(pos, quat, cur_pos[i]) + v_g
+                    tar = tars[i]
                 else:
                     v_g = R @ f_interp[i][:, t] + vel * D.DT
                     tar = (pos + R @ cur_pos[i]) + v_g

@@ -1173,6 +1173,41 @@ void pgo_set_param(void* h, const char* name, double v) {
   fprintf(stderr, "pgo_set_param: unknown %s\n", name);
 }
 
+// pybullet.multiplyTransforms(posA, ornA, posB, identity)[0] in SINGLE precision, as b3MultiplyTransforms computes it (b3Transform with
+// float b3Scalar): b3Quaternion::length2, b3Matrix3x3::setRotation, b3Transform::operator() -- every operation one float operation in
+// b3's order (this file is compiled with -ffp-contract=off).  See oracle/envsim.py b3_multiply_transforms (the numpy statement of the
+// same arithmetic, kept as the documented definition and cross-checked against this one by tests/test_oracle_cpu.py).
+void pgo_b3_multiply_transforms(const double* posA, const double* ornA, const double* posB, double* out) {
+  const float x = (float)ornA[0], y = (float)ornA[1], z = (float)ornA[2], w = (float)ornA[3];
+  const float xx0 = x * x, yy0 = y * y, zz0 = z * z, ww0 = w * w;
+  float d = xx0 + yy0; d = d + zz0; d = d + ww0;
+  const float s = 2.0f / d;
+  const float xs = x * s, ys = y * s, zs = z * s;
+  const float wx = w * xs, wy = w * ys, wz = w * zs;
+  const float xx = x * xs, xy = x * ys, xz = x * zs;
+  const float yy = y * ys, yz = y * zs, zz = z * zs;
+  const float t0 = yy + zz, t1 = xx + zz, t2 = xx + yy;
+  const float R[3][3] = {{1.0f - t0, xy - wz, xz + wy}, {xy + wz, 1.0f - t1, yz - wx}, {xz - wy, yz + wx, 1.0f - t2}};
+  const float v0 = (float)posB[0], v1 = (float)posB[1], v2 = (float)posB[2];
+  for (int i = 0; i < 3; i++) {
+    const float a = v0 * R[i][0], b = v1 * R[i][1], c = v2 * R[i][2];
+    float acc = a + b; acc = acc + c; acc = acc + (float)posA[i];
+    out[i] = (double)acc;
+  }
+}
+
+// plate_env:526-530 for both fingers in one call: target = multiplyTransforms(pos, quat, cur_fin) + (multiplyTransforms(0, quat, f) + vel * dt),
+// the transforms in single precision (above), the sums in double in the env's order
+void pgo_servo_targets(const double* pose7, const double* cur_pos6, const double* f6, const double* vel3, double dt, double* out6) {
+  const double zero[3] = {0, 0, 0};
+  for (int i = 0; i < 2; i++) {
+    double v32[3], t32[3];
+    pgo_b3_multiply_transforms(zero, pose7 + 3, f6 + 3 * i, v32);
+    pgo_b3_multiply_transforms(pose7, pose7 + 3, cur_pos6 + 3 * i, t32);
+    for (int k = 0; k < 3; k++) { double vg = v32[k] + vel3[k] * dt; out6[3 * i + k] = t32[k] + vg; }
+  }
+}
+
 // add a body; returns index.  type 0 box (half), 1 hull (verts), 2 cylinder (half = r, r, halfh)
 int pgo_add_body(void* h, int type, const double* half, const double* verts, int nverts, double mass,
                  const double* pos, const double* quat, double friction, int compound, double margin) {

@@ -343,3 +343,14 @@ def test_tip_records_reproduce_recorded_tip_data(exp):
                 np.testing.assert_array_equal(got[rows, f, :3], raw[rows, f, :3])
             if on[j][f]:
                 assert np.abs(got[rows, f, 3:] - raw[rows, f, 3:]).max() <= (2e-7 if exp == "plate_20.0" else 0.0)
+
+
+def test_single_precision_multiply_transforms_native_equals_numpy_statement():
+    """oracle/envsim.py b3_multiply_transforms (numpy float32, the documented definition) == the C++ copy EnvSim calls."""
+    from oracle.envsim import EnvSim, b3_multiply_transforms, b3_multiply_transforms_native
+    sim = EnvSim(oracle_spec(make_spec("foodbox")), 20.0)
+    rng = np.random.RandomState(3)
+    for _ in range(2000):
+        p = rng.randn(3); q = rng.randn(4); q /= np.linalg.norm(q) * rng.uniform(0.999999, 1.000001)
+        v = rng.randn(3) * rng.choice([1e-3, 0.1, 1.0, 100.0])
+        np.testing.assert_array_equal(b3_multiply_transforms(p, q, v), b3_multiply_transforms_native(sim.L, p, q, v))
