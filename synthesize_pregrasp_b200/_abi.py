@@ -155,10 +155,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("PREGRASP_B200_LIB", LIB_PATH)     # override: kernel-variant experiments only
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback)")
-    L = C.CDLL(os.environ.get("PREGRASP_B200_LIB", LIB_PATH))     # override: kernel-variant experiments only
+    L = C.CDLL(path)
     vp, i32, f64 = C.c_void_p, C.c_int, C.c_double
     L.pg_last_error.restype = C.c_char_p
     L.pg_version.restype = C.c_char_p

@@ -48,7 +48,8 @@ struct Blob {
 extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   if (!sp || !out) { set_error("pg_env_create: null argument"); return PG_ERR_INVALID; }
   if (sp->n_static < 1 || sp->n_static > MAX_STATICS || sp->n_regions > MAX_REGIONS || sp->n_states > MAX_STATES ||
-      sp->n_cloud != P_CLOUD || sp->n_crop < 1 || sp->n_crop > 2 || sp->n_dist_box > 4 || !sp->cloud || !sp->csg) {
+      sp->n_cloud != P_CLOUD || sp->n_crop < 1 || sp->n_crop > 2 || sp->n_dist_box < 0 || sp->n_dist_box > 4 || sp->n_dist_tri < 0 ||
+      (sp->n_dist_tri > 0 && !sp->dist_tri) || !sp->cloud || !sp->csg) {
     set_error("pg_env_create: spec out of supported bounds"); return PG_ERR_INVALID;
   }
   int ndev = 0;
@@ -83,7 +84,7 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
     size_t idx = ((size_t)(k / 4) * C3 + n) * 4 + (k % 4);
     w3hi[idx] = hi; w3lo[idx] = wv - hi;
   }
-  e->use_tensor_cores = getenv("PG_COST_FFMA") ? 0 : 1;
+  e->use_tensor_cores = 1;
   Blob b;
   size_t o_env = b.add(&E, sizeof(EnvDev));
   size_t o_cloud = b.add(sp->cloud, sizeof(double) * 3 * P_CLOUD);
@@ -148,6 +149,8 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
     pk_quat_to_matrix(bx.quat, c.clear_R[w]);
   }
   for (int i = 0; i < 3; i++) c.clear_size[i] = sp->clearance_wall_size[i];
+  ce = cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) { cudaFree(d); delete e; return cuda_fail(ce, "cudaStreamCreate"); }
   *out = e;
   return PG_OK;
 }
@@ -158,6 +161,7 @@ extern "C" int pg_env_destroy(PgEnv* e) {
   cudaFree(e->blob); cudaFree(e->pose); cudaFree(e->fins); cudaFree(e->logit); cudaFree(e->latent); cudaFree(e->path_dev);
   cudaFree(e->u_stage); cudaFree(e->noise_stage); cudaFree(e->J_stage); cudaFree(e->metric_stage); cudaFree(e->trace_stage);
   cudaFree(e->regroup);
+  if (e->host_stream) cudaStreamDestroy(e->host_stream);
   delete e;
   return PG_OK;
 }
@@ -166,6 +170,7 @@ static int ensure_scratch(PgEnv* e, size_t evals) {
   if (e->cap_evals >= evals && e->path_dev) return PG_OK;
   cudaFree(e->pose); cudaFree(e->fins); cudaFree(e->logit); cudaFree(e->latent);
   e->pose = e->fins = nullptr; e->logit = e->latent = nullptr;
+  e->cap_evals = 0;                                  // a failed allocation below must not leave a stale capacity behind
   PG_CUDA(cudaMalloc(&e->pose, evals * 7 * sizeof(double)));
   PG_CUDA(cudaMalloc(&e->fins, evals * 6 * sizeof(double)));
   PG_CUDA(cudaMalloc(&e->logit, evals * sizeof(float)));
@@ -275,7 +280,7 @@ extern "C" int pg_rollout_host(PgEnv* e, const double* u_host, const float* nois
     PG_CUDA(cudaMalloc(&e->trace_stage, tr * sizeof(double)));
     e->cap_stage_trace = tr;
   }
-  cudaStream_t st = 0;
+  cudaStream_t st = e->host_stream;                 // the handle's own stream: host-buffer calls on different handles overlap
   PG_CUDA(cudaMemcpyAsync(e->u_stage, u_host, (size_t)N * ADIM * sizeof(double), cudaMemcpyHostToDevice, st));
   if (noise_host) PG_CUDA(cudaMemcpyAsync(e->noise_stage, noise_host, (size_t)K * N * ADIM * sizeof(float), cudaMemcpyHostToDevice, st));
   rc = pg_rollout(e, e->u_stage, noise_host ? e->noise_stage : nullptr, K, N, path_host, max_force, e->J_stage,

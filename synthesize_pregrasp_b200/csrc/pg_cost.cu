@@ -453,12 +453,9 @@ int launch_cost(PgEnv* env, const double* pose, const double* fins, int B, float
     return launch_mlp(env, latent, B, logit, st);
   }
   size_t smem = sizeof(Smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PG_CUDA(cudaFuncSetAttribute(pcn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PG_CUDA(cudaFuncSetAttribute(pcn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // per-device opt-in, set on every launch (an env may live on any device of the process)
+  PG_CUDA(cudaFuncSetAttribute(pcn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PG_CUDA(cudaFuncSetAttribute(pcn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count(env->device);
   if (grid > B) grid = B;
   pcn_kernel<true><<<grid, NT, smem, st>>>(env->cost, pose, fins, nullptr, nullptr, nullptr, nullptr, B, env->cost.n_cloud, latent);

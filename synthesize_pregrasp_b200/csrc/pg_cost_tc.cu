@@ -431,11 +431,8 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
 // ---------------------------------------------------------------------------------------------------------
 int launch_cost_tc(PgEnv* env, const double* pose, const double* fins, int B, float* latent, cudaStream_t st) {
   size_t smem = sizeof(TcSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PG_CUDA(cudaFuncSetAttribute(pcn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // the opt-in is per device and an env may live on any device of the process: set it on every launch (host-side, cheap)
+  PG_CUDA(cudaFuncSetAttribute(pcn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->device);
   int grid = sms < B ? sms : B;

@@ -17,6 +17,18 @@ static inline int build_envdev(const PgEnvSpec* sp, EnvDev& E, std::string& err)
   if (sp->n_static < 1 || sp->n_static > MAX_STATICS || sp->n_regions > MAX_REGIONS || sp->n_states > MAX_STATES || !sp->csg) {
     err = "spec out of supported bounds"; return PG_ERR_INVALID;
   }
+  if (sp->n_regions < 0 || sp->n_states < 1 || sp->n_clear_walls < 0 || sp->n_clear_walls > 2 || sp->floor_index < 0 || sp->floor_index >= sp->n_static ||
+      sp->settle_substeps < 0 || sp->metric_axis < 0 || sp->metric_axis > 2) { err = "negative / out-of-range count or index in the spec"; return PG_ERR_INVALID; }
+  for (int w = 0; w < sp->n_clear_walls; w++)
+    if (sp->clear_walls[w] < 0 || sp->clear_walls[w] >= sp->n_static) { err = "clear_walls index out of range"; return PG_ERR_INVALID; }
+  if (sp->region_type != REGION_MESH && sp->region_type != REGION_BLOCK && sp->region_type != REGION_BOTTLE) { err = "unknown region type"; return PG_ERR_INVALID; }
+  for (int i = 0; i < sp->n_states * NFING; i++) {
+    // region ids are 1-based; 0 / negative ids wrap like the reference's python indexing (region_parse)
+    const int rid = sp->csg[i] - 1, nreg = sp->region_type == REGION_BOTTLE ? 4 : sp->n_regions;
+    if (rid >= nreg || rid < -nreg) { err = "contact-state graph names a region outside the region table"; return PG_ERR_INVALID; }
+  }
+  if (sp->region_type == REGION_MESH && (!sp->tri_v || !sp->region_n)) { err = "mesh regions need tri_v and region_n"; return PG_ERR_INVALID; }
+  if (sp->region_type == REGION_BLOCK && (!sp->block_r || !sp->block_axis || !sp->region_n)) { err = "block regions need block_r, block_axis and region_n"; return PG_ERR_INVALID; }
   memset(&E, 0, sizeof(EnvDev));
   // ---- PyBullet server defaults confirmed by the recorded trajectories
   E.dt = 1.0 / 250.0; E.gravity_z = -10.0; E.erp = 0.2; E.erp2 = 0.08; E.slop = 1e-5; E.residual_threshold = 1e-7;

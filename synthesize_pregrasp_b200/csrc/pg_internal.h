@@ -54,6 +54,7 @@ struct PgEnv {
   size_t cap_evals;
   double *u_stage; float* noise_stage; double *J_stage, *metric_stage, *trace_stage;   // pg_rollout_host staging
   size_t cap_stage_K, cap_stage_trace;
+  cudaStream_t host_stream;            // pg_rollout_host: copies + kernels of one handle run on its own stream
   void* regroup; size_t cap_regroup;   // settle-phase exchange buffer of the rollout kernel ([K] RegroupSlot)
 };
 

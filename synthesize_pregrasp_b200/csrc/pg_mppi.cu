@@ -8,7 +8,8 @@
 
 namespace pg {
 
-#define MP_THREADS 384          // 4 row-groups x 96 columns when N*D = 96
+#define MP_THREADS 256
+#define MP_MAX_ND 1536          // N <= 32 env steps x D = 48 (the rollout ABI's limit)
 
 __global__ void mppi_min_kernel(const double* __restrict__ J, int K, double* __restrict__ block_min) {
   double m = INFINITY;
@@ -23,59 +24,101 @@ __global__ void mppi_min_kernel(const double* __restrict__ J, int K, double* __r
   }
 }
 
-// partial layout per block: [0] sum w, [1] sum J, [2..2+ND) sum w*E
+// Streams a contiguous chunk of rows (rollouts).  Per tile of MP_THREADS rows every thread computes ONE weight (fp64 exp is
+// ~100 instructions; the columns of a row share it through shared memory), then thread (g, c) accumulates column slot c
+// (VEC consecutive floats, one 16-byte load when VEC = 4) over the rows g, g + groups, ... of the tile.  Fixed order
+// everywhere: the result does not depend on scheduling.   partial layout per block: [0] sum w, [1] sum J, [2..2+ND) sum w*E
+template <int VEC>
 __global__ void __launch_bounds__(MP_THREADS)
 mppi_accum_kernel(const double* __restrict__ J, const float* __restrict__ noise, int K, int ND, double kappa,
                   const double* __restrict__ block_min, int n_min, int rows_per_block, double* __restrict__ partial) {
   __shared__ double s_min;
-  __shared__ double s_acc[MP_THREADS];
-  __shared__ double s_w[4], s_j[4];
-  if (threadIdx.x == 0) {
+  __shared__ double s_wt[MP_THREADS];            // weights of the current tile of rows
+  __shared__ double s_acc[MP_MAX_ND];            // [groups][ND] partial sums (groups * ND <= max(MP_THREADS * VEC, ND))
+  __shared__ double s_red[2][MP_THREADS / 32];
+  const int t = threadIdx.x;
+  if (t == 0) {
     double m = block_min[0];
     for (int i = 1; i < n_min; i++) m = fmin(m, block_min[i]);
     s_min = m;
   }
   __syncthreads();
   const double jmin = s_min;
-  const int groups = MP_THREADS / ND;            // row groups handled concurrently
-  const int g = threadIdx.x / ND, d = threadIdx.x % ND;
-  int r0 = blockIdx.x * rows_per_block, r1 = min(K, r0 + rows_per_block);
-  double acc = 0, sw = 0, sj = 0;
-  if (g < groups) {
-    for (int r = r0 + g; r < r1; r += groups) {
-      double jr = J[r];
-      double w = exp(-kappa * (jr - jmin));      // +inf cost -> weight 0
-      acc += w * (double)__ldg(noise + (size_t)r * ND + d);
-      if (d == 0) { sw += w; sj += jr; }
-    }
-  }
-  s_acc[threadIdx.x] = acc;
-  if (g < groups && d == 0) { s_w[g] = sw; s_j[g] = sj; }
-  __syncthreads();
+  const int slots = ND / VEC;                              // column slots
+  const int ct = slots < MP_THREADS ? slots : MP_THREADS;  // threads per row group
+  const int groups = MP_THREADS / ct;
+  const int g = t / ct, c_in = t % ct;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(K, r0 + rows_per_block);
+  double sw = 0, sj = 0;
   double* out = partial + (size_t)blockIdx.x * (2 + ND);
-  if (threadIdx.x < ND) {
-    double v = 0;
-    for (int q = 0; q < groups; q++) v += s_acc[q * ND + threadIdx.x];
-    out[2 + threadIdx.x] = v;
+  for (int c0 = 0; c0 < slots; c0 += ct) {                 // one pass unless N*D/VEC > MP_THREADS
+    const int c = c0 + c_in;
+    const bool col_ok = (g < groups) && (c < slots);
+    double acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) acc[v] = 0;
+    for (int tile = r0; tile < r1; tile += MP_THREADS) {
+      const int nrow = min(MP_THREADS, r1 - tile);
+      __syncthreads();                                     // previous tile's weights are consumed
+      double w = 0;
+      if (t < nrow) {
+        const double jr = J[tile + t];
+        w = exp(-kappa * (jr - jmin));                     // +inf cost -> weight 0
+        if (c0 == 0) { sw += w; sj += jr; }
+      }
+      s_wt[t] = w;
+      __syncthreads();
+      if (col_ok) {
+        const float* base = noise + (size_t)tile * ND + (size_t)c * VEC;
+        for (int r = g; r < nrow; r += groups) {
+          const double wr = s_wt[r];
+          if constexpr (VEC == 4) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(base + (size_t)r * ND));
+            acc[0] += wr * (double)e.x; acc[1] += wr * (double)e.y; acc[2] += wr * (double)e.z; acc[3] += wr * (double)e.w;
+          } else {
+            acc[0] += wr * (double)__ldg(base + (size_t)r * ND);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (col_ok) {
+#pragma unroll
+      for (int v = 0; v < VEC; v++) s_acc[g * (ct * VEC) + c_in * VEC + v] = acc[v];
+    }
+    __syncthreads();
+    for (int i = t; i < ct * VEC && c0 * VEC + i < ND; i += MP_THREADS) {
+      double v = 0;
+      for (int q = 0; q < groups; q++) v += s_acc[q * (ct * VEC) + i];
+      out[2 + c0 * VEC + i] = v;
+    }
+    __syncthreads();                                       // s_acc is rewritten by the next column pass
   }
-  if (threadIdx.x == 0) {
+  // sum w, sum J: warp shuffle tree, then the warps in index order
+  for (int o = 16; o > 0; o >>= 1) { sw += __shfl_xor_sync(0xffffffffu, sw, o); sj += __shfl_xor_sync(0xffffffffu, sj, o); }
+  if ((t & 31) == 0) { s_red[0][t >> 5] = sw; s_red[1][t >> 5] = sj; }
+  __syncthreads();
+  if (t == 0) {
     double a = 0, b = 0;
-    for (int q = 0; q < groups; q++) { a += s_w[q]; b += s_j[q]; }
+    for (int q = 0; q < MP_THREADS / 32; q++) { a += s_red[0][q]; b += s_red[1][q]; }
     out[0] = a; out[1] = b;
   }
 }
 
+// folds the per-block partials: thread d sums column d over the blocks in index order; warp 0 sums (sum w, sum J) with a
+// fixed lane-strided order + shuffle tree
 __global__ void mppi_final_kernel(const double* __restrict__ partial, int nblocks, int ND, const double* __restrict__ block_min,
                                   int n_min, double alpha, double* __restrict__ u, double* __restrict__ out, int apply) {
   __shared__ double s_sw;
-  int t = threadIdx.x;
-  if (t == 0) {
-    double m = block_min[0];
-    for (int i = 1; i < n_min; i++) m = fmin(m, block_min[i]);
+  const int t = threadIdx.x;
+  if (t < 32) {
     double a = 0, b = 0;
-    for (int i = 0; i < nblocks; i++) { a += partial[(size_t)i * (2 + ND)]; b += partial[(size_t)i * (2 + ND) + 1]; }
-    s_sw = a;
-    if (out) { out[0] = m; out[1] = a; out[2] = b; }
+    for (int i = t; i < nblocks; i += 32) { a += partial[(size_t)i * (2 + ND)]; b += partial[(size_t)i * (2 + ND) + 1]; }
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    double m = INFINITY;
+    for (int i = t; i < n_min; i += 32) m = fmin(m, block_min[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (t == 0) { s_sw = a; if (out) { out[0] = m; out[1] = a; out[2] = b; } }
   }
   __syncthreads();
   for (int d = t; d < ND; d += blockDim.x) {
@@ -90,38 +133,37 @@ __global__ void mppi_final_kernel(const double* __restrict__ partial, int nblock
 
 using namespace pg;
 
-static double* g_scratch[16] = {nullptr};
-static size_t g_scratch_cap[16] = {0};
-
 extern "C" int pg_mppi_update(const double* J_dev, const float* noise_dev, int K, int N, int D, double kappa, double alpha,
                               double* u_inout_dev, double* partial_dev, int apply, void* stream) {
   if (!J_dev || !noise_dev || K <= 0 || N <= 0 || D <= 0) { set_error("pg_mppi_update: bad arguments"); return PG_ERR_INVALID; }
-  int ND = N * D;
-  if (ND > MP_THREADS) { set_error("pg_mppi_update: N*D > 384 not supported"); return PG_ERR_INVALID; }
+  const int ND = N * D;
+  if (ND > MP_MAX_ND) { set_error("pg_mppi_update: N*D > 1536 not supported"); return PG_ERR_INVALID; }
   if (apply && !u_inout_dev) { set_error("pg_mppi_update: apply without u"); return PG_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0;
   PG_CUDA(cudaGetDevice(&dev));
   int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  PG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int nblocks = sms * 4;
   int rows_per_block = (K + nblocks - 1) / nblocks;
-  if (rows_per_block < 32) { rows_per_block = 32; }
+  if (rows_per_block < 32) rows_per_block = 32;
   nblocks = (K + rows_per_block - 1) / rows_per_block;
   int n_min = (K + 1023) / 1024;
   if (n_min > sms) n_min = sms;
-  size_t need = (size_t)nblocks * (2 + ND) + n_min;
-  if (dev < 16 && g_scratch_cap[dev] < need) {
-    if (g_scratch[dev]) cudaFree(g_scratch[dev]);
-    PG_CUDA(cudaMalloc(&g_scratch[dev], need * sizeof(double)));
-    g_scratch_cap[dev] = need;
-  }
-  double* partial = g_scratch[dev];
+  // scratch from the stream-ordered pool: no process-global state, safe with several devices / threads / streams
+  const size_t need = (size_t)nblocks * (2 + ND) + n_min;
+  double* partial = nullptr;
+  PG_CUDA(cudaMallocAsync(&partial, need * sizeof(double), st));
   double* bmin = partial + (size_t)nblocks * (2 + ND);
   mppi_min_kernel<<<n_min, 256, 0, st>>>(J_dev, K, bmin); count_launch();
-  mppi_accum_kernel<<<nblocks, MP_THREADS, 0, st>>>(J_dev, noise_dev, K, ND, kappa, bmin, n_min, rows_per_block, partial); count_launch();
-  mppi_final_kernel<<<1, 128, 0, st>>>(partial, nblocks, ND, bmin, n_min, alpha, u_inout_dev, partial_dev, apply); count_launch();
-  PG_CUDA(cudaGetLastError());
+  const bool vec4 = (ND % 4 == 0) && ((reinterpret_cast<uintptr_t>(noise_dev) & 15) == 0);
+  if (vec4) mppi_accum_kernel<4><<<nblocks, MP_THREADS, 0, st>>>(J_dev, noise_dev, K, ND, kappa, bmin, n_min, rows_per_block, partial);
+  else mppi_accum_kernel<1><<<nblocks, MP_THREADS, 0, st>>>(J_dev, noise_dev, K, ND, kappa, bmin, n_min, rows_per_block, partial);
+  count_launch();
+  mppi_final_kernel<<<1, 256, 0, st>>>(partial, nblocks, ND, bmin, n_min, alpha, u_inout_dev, partial_dev, apply); count_launch();
+  cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(partial, st);
+  if (le != cudaSuccess) return cuda_fail(le, "pg_mppi_update launch");
   return PG_OK;
 }
 

@@ -64,7 +64,20 @@ struct Sim {
   int obj_first;         // reset substep: object proxy is older than the walls'
   int last_iterations;
   int sync_cta;          // hull kernel: all threads of the CTA run rollouts, so substeps may start on a CTA barrier
+#if defined(PG_PHASE_CLOCKS)
+  long long clk[6];      // profiling builds: cycles in collide / external / solver set-up / sweeps / integrate / rest
+#endif
 };
+// profiling builds (-DPG_PHASE_CLOCKS, csrc/build_variant.sh + tools/gpu_phase_clocks.py): where a rollout's cycles go
+#if defined(PG_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+#define PG_CLK(S, slot, t0) { long long _t = clock64(); (S).clk[slot] += _t - (t0); (t0) = _t; }
+#define PG_CLK0(t0) long long t0 = clock64()
+#define PG_CLK_RESET(t0) t0 = clock64()
+#else
+#define PG_CLK(S, slot, t0)
+#define PG_CLK0(t0)
+#define PG_CLK_RESET(t0)
+#endif
 
 // -------------------------------------------------------------------------------------------------
 PG_HD bool is_static(int b) { return b < MAX_STATICS; }
@@ -719,6 +732,7 @@ PG_HD void bt_quicksort(int* key, int* val, int n) {
 }
 
 PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* __restrict__ statR, RowSet& __restrict__ rs, double* sm, int ss) {
+  PG_CLK0(S_t0);
   // islands over the (overlapping-pair) manifolds; tags: obj 0, tip0 1, tip1 2
   int uf[3] = {0, 1, 2};
   for (int k = 0; k < S.nman; k++) {
@@ -798,6 +812,7 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
     c_hi[isl] = rs.nc.n;
   }
   S.last_iterations = 0;
+  PG_CLK(S, 2, S_t0);
 #if defined(PG_HOST_STATS) && !defined(__CUDA_ARCH__)
   { extern long g_stat_pts[32], g_stat_nc[16]; g_stat_pts[rs.n_pts < 31 ? rs.n_pts : 31]++; g_stat_nc[rs.nc.n < 15 ? rs.nc.n : 15]++; }
 #endif
@@ -952,6 +967,7 @@ PG_HDN void solve(const EnvDev& __restrict__ E, Sim& __restrict__ S, const M3* _
   if (it > it_max) it_max = it;
   }
   S.last_iterations = it_max;
+  PG_CLK(S, 3, S_t0);
   for (int d = 0; d < 3; d++) {
     DynBody& b = S.dyn[d];
     V3 w = sm_w(sm, ss, d), v = sm_v(sm, ss, d);
@@ -990,13 +1006,18 @@ PG_HDN void substep(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, double
   if (S.sync_cta) __syncthreads();
 #endif
 #endif
+  PG_CLK0(t0);
   collide<SHAPE>(E, S, statR);
 #if defined(__CUDA_ARCH__) && defined(PG_SUBSTEP_BARRIER)
   if (S.sync_cta) __syncthreads();
 #endif
+  PG_CLK(S, 0, t0);
   apply_external(E, S);
+  PG_CLK(S, 1, t0);
   solve(E, S, statR, rs, sm, ss);
+  PG_CLK_RESET(t0);
   integrate(E, S);
+  PG_CLK(S, 4, t0);
 }
 
 PG_HD void drop_manifolds_of(Sim& S, int body) {

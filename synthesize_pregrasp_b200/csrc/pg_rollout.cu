@@ -28,9 +28,7 @@ int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N
     PG_CUDA(cudaMalloc(&env->regroup, need));
     env->cap_regroup = need;
   }
-  static int use_regroup = -1;                                 // PG_REGROUP=0 switches the regrouping off (tuning only)
-  if (use_regroup < 0) { const char* v = getenv("PG_REGROUP"); use_regroup = (v && atoi(v) == 0) ? 0 : 1; }
-  void* regroup = use_regroup ? env->regroup : nullptr;
+  void* regroup = env->regroup;
   int rc;
   if (env->host_env.obj_shape != SHAPE_BOX)
     rc = launch_rollout_hull(st, env->dev_env, u, noise, K, N, path_dev, max_force, pose, fins, metric, trace, iters, prob_dev, regroup);

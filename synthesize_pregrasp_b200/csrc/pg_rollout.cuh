@@ -215,6 +215,10 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
       t.half = V3(E.tip_half[f][0], E.tip_half[f][1], E.tip_half[f][2]); t.friction = E.tip_friction;
     }
   }
+#if defined(PG_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+  for (int i = 0; i < 6; i++) S.clk[i] = 0;
+  PG_CLK0(roll_t0);
+#endif
   S.nman = 0; S.filter_off = 0; S.obj_first = 1; S.last_iterations = 0; S.early = 0; S.sync_cta = out.sync_cta;
   for (int f = 0; f < 2; f++) { S.plo[f] = V3(); S.phi[f] = V3(); }
   S.cons[0].active = 0; S.cons[1].active = 0;
@@ -268,8 +272,14 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
         S.cons[i].pivotB = tar; S.cons[i].frameB = R; S.cons[i].max_impulse = max_force * E.dt;
       }
       substep<SHAPE>(E, S, statR, rs, sm, ss);
+#if !defined(PG_PHASE_CLOCKS)
       if (out.iters) out.iters[j * SKIP + t] = S.last_iterations;
+#endif
+#if defined(PG_REGROUP_EVERY)
+      solver_work += S.last_iterations * (12 + 2 * rs.n_pts);    // sweeps x rows
+#else
       solver_work += S.last_iterations;
+#endif
     }
     for (int i = 0; i < NFING; i++) {
       out.fins[(j * NFING + i) * 3 + 0] = cur_pos[i].x;
@@ -282,8 +292,18 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
 #if defined(__CUDA_ARCH__)
       if (out.regroup) settle_regroup(S, m0, out, solver_work);     // from here on this thread may run another rollout of its CTA
 #endif
+#if defined(PG_REGROUP_EVERY)
+      int recent_work = 0;                              // solver work since the last re-deal
+#endif
       for (int s = 0; s < E.settle_substeps; s++) {
+#if defined(__CUDA_ARCH__) && defined(PG_REGROUP_EVERY)
+        // the kind of a rollout drifts while it settles: re-deal again every PG_REGROUP_EVERY substeps by the work just seen
+        if (out.regroup && s > 0 && s % PG_REGROUP_EVERY == 0) { settle_regroup(S, m0, out, recent_work); recent_work = 0; }
+#endif
         substep<SHAPE>(E, S, statR, rs, sm, ss);
+#if defined(PG_REGROUP_EVERY)
+        recent_work += S.last_iterations * (12 + 2 * rs.n_pts);
+#endif
         if (out.settle_iters) out.settle_iters[s] = S.last_iterations;
       }
       if (out.metric) *out.metric = m0 + (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
@@ -292,6 +312,15 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
     double* p = out.pose + j * 7;
     p[0] = o.pos.x; p[1] = o.pos.y; p[2] = o.pos.z; p[3] = o.q.x; p[4] = o.q.y; p[5] = o.q.z; p[6] = o.q.w;
   }
+#if defined(PG_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+  // profiling builds: lane 0 of every warp adds its phase cycles to the counters behind out.iters (6 x unsigned long long)
+  if (out.iters && (threadIdx.x & 31) == 0) {
+    long long total = clock64() - roll_t0, sum = 0;
+    unsigned long long* g = (unsigned long long*)out.iters;
+    for (int i = 0; i < 5; i++) { atomicAdd(g + i, (unsigned long long)S.clk[i]); sum += S.clk[i]; }
+    atomicAdd(g + 5, (unsigned long long)(total - sum));
+  }
+#endif
 }
 
 }  // namespace pg

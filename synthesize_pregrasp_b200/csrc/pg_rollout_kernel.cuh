@@ -4,7 +4,9 @@
 #ifndef PG_BLOCK_THREADS
 #define PG_BLOCK_THREADS 448
 #endif
+#ifndef PG_NO_SUBSTEP_BARRIER
 #define PG_SUBSTEP_BARRIER 1     // CTA barriers inside substep() (pg_physics.cuh): the warps of a CTA walk the collision code together
+#endif
 #include <cstdlib>
 #include "pg_internal.h"
 #include "pg_rollout.cuh"
@@ -41,7 +43,11 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const
     out.fins = fins + (size_t)k * N * NFING * 3;
     out.metric = metric ? metric + k : nullptr;
     out.trace = trace ? trace + (size_t)k * N * SKIP * 7 : nullptr;
+#if defined(PG_PHASE_CLOCKS)
+    out.iters = iters;                                         // profiling builds: 6 global cycle counters (tools/gpu_phase_clocks.py)
+#else
     out.iters = iters ? iters + (size_t)k * N * SKIP : nullptr;
+#endif
     out.settle_iters = nullptr;
     out.sync_cta = cta_full;
     out.regroup = (cta_full && lanes == 32 && blockDim.x > 32) ? regroup : nullptr;
@@ -62,18 +68,13 @@ static int launch_rollout_sized(cudaStream_t st, const EnvDev* env, const double
                                 double max_force, double* pose, double* fins, double* metric, double* trace, int* iters, const int* prob,
                                 void* regroup) {
   const size_t smem = SM_DOUBLES * RK_THREADS * sizeof(double);
-  static int sm_of[64] = {0};                                  // per device: SM count, and the one-time shared-memory opt-in
-  int dev = 0; PG_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) dev = 0;
-  if (!sm_of[dev]) {
-    PG_CUDA(cudaFuncSetAttribute(rollout_kernel<SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PG_CUDA(cudaDeviceGetAttribute(&sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
-  }
-  const int n_sm = sm_of[dev], max_warps = RK_THREADS / 32;
+  int dev = 0, n_sm = 0;
+  PG_CUDA(cudaGetDevice(&dev));
+  // per-device opt-in and SM count, queried on every launch (host-side, cheap; no process-global state)
+  PG_CUDA(cudaFuncSetAttribute(rollout_kernel<SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PG_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  const int max_warps = RK_THREADS / 32;
   int lanes = (K + n_sm - 1) / n_sm;                           // one warp per SM first, then fill its lanes, then add warps
-  static int lanes_env = -1;                                   // PG_LANES overrides (tuning only)
-  if (lanes_env < 0) { const char* v = getenv("PG_LANES"); lanes_env = v ? atoi(v) : 0; }
-  if (lanes_env > 0) lanes = lanes_env;
   if (lanes < 1) lanes = 1;
   if (lanes > 32) lanes = 32;
   const int warps = (K + lanes - 1) / lanes;

@@ -175,6 +175,16 @@ def test_mppi_update_kernel(EN):
         EN.mppi_update(torch.as_tensor(J, device="cuda:0"), torch.as_tensor(E, device="cuda:0"), u_t, 5.0, 1.0)
         ref, _ = mppi.mppi_update(np.zeros((2, 48)), J, E, 5.0, 1.0)
         np.testing.assert_allclose(u_t.cpu().numpy(), ref, rtol=0, atol=1e-12)
+    # every horizon the rollout ABI accepts (N <= 32): N*D = 48 ... 1536 columns, vectorised and scalar column paths
+    for N, D in ((1, 48), (3, 48), (8, 48), (32, 48), (2, 7), (1, 1)):
+        K = 777
+        J = rng.normal(0, 1, K); E = rng.randn(K, N, D).astype(np.float32)
+        J[5::11] = np.inf
+        u0 = rng.randn(N, D)
+        u_t = torch.as_tensor(u0, device="cuda:0").clone()
+        EN.mppi_update(torch.as_tensor(J, device="cuda:0"), torch.as_tensor(E, device="cuda:0"), u_t, 5.0, 1.0)
+        ref, _ = mppi.mppi_update(u0, J, E, 5.0, 1.0)
+        np.testing.assert_allclose(u_t.cpu().numpy(), ref, rtol=0, atol=1e-12, err_msg=f"N={N} D={D}")
     K = 1 << 20
     E = torch.randn((K, 2, 48), device="cuda:0", dtype=torch.float32)
     u_t = torch.zeros((2, 48), dtype=torch.float64, device="cuda:0")
