@@ -76,13 +76,32 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   for (int j = 0; j < C1; j++) w1d[j] = W.conv1_w[4 * j + 3];
   for (int c = 0; c < C2; c++) for (int j = 0; j < C1; j++) w2t[j * C2 + c] = W.conv2_w[c * C1 + j];
   for (int o = 0; o < C3; o++) for (int k = 0; k < C2; k++) { w3at[k * C3 + o] = W.conv3_w[o * 2 * C2 + k]; w3bt[k * C3 + o] = W.conv3_w[o * 2 * C2 + C2 + k]; }
-  // tensor-core operands: W3a split into tf32 hi + lo, canonical K-major layout [(k/4)][n][k%4]
-  std::vector<float> w3hi(C2 * C3), w3lo(C2 * C3);
+  // tensor-core operands (pg_cost_tc.cu): tf32 hi + lo splits in the canonical K-major layout [(k/4)][n][k%4].
+  // conv2 has no activation (network.py:402-404), so conv3's point half is folded:  W3a (W2 h1 + b2) = (W3a W2) h1 + W3a b2
   auto tf32_rna = [](float x) { uint32_t u; memcpy(&u, &x, 4); u += 0x1000u; u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; };
-  for (int n = 0; n < C3; n++) for (int k = 0; k < C2; k++) {
-    float wv = W.conv3_w[n * 2 * C2 + k], hi = tf32_rna(wv);
-    size_t idx = ((size_t)(k / 4) * C3 + n) * 4 + (k % 4);
-    w3hi[idx] = hi; w3lo[idx] = wv - hi;
+  const int N4 = 32;
+  std::vector<float> w32hi(C1 * C3), w32lo(C1 * C3), w2hi(C1 * C2), w2lo(C1 * C2), w4hi(C3 * N4, 0.f), w4lo(C3 * N4, 0.f), cbase(C3);
+  for (int o = 0; o < C3; o++) {
+    double bb = 0;
+    for (int c = 0; c < C2; c++) bb += (double)W.conv3_w[o * 2 * C2 + c] * (double)W.conv2_b[c];
+    cbase[o] = (float)((double)W.conv3_b[o] + bb);
+    for (int j = 0; j < C1; j++) {
+      double acc = 0;
+      for (int c = 0; c < C2; c++) acc += (double)W.conv3_w[o * 2 * C2 + c] * (double)W.conv2_w[c * C1 + j];
+      const float wv = (float)acc, hi = tf32_rna(wv);
+      const size_t idx = ((size_t)(j / 4) * C3 + o) * 4 + (j % 4);
+      w32hi[idx] = hi; w32lo[idx] = wv - hi;
+    }
+  }
+  for (int c = 0; c < C2; c++) for (int j = 0; j < C1; j++) {
+    const float wv = W.conv2_w[c * C1 + j], hi = tf32_rna(wv);
+    const size_t idx = ((size_t)(j / 4) * C2 + c) * 4 + (j % 4);
+    w2hi[idx] = hi; w2lo[idx] = wv - hi;
+  }
+  for (int q = 0; q < C4; q++) for (int o = 0; o < C3; o++) {
+    const float wv = W.conv4_w[q * C3 + o], hi = tf32_rna(wv);
+    const size_t idx = ((size_t)(o / 4) * N4 + q) * 4 + (o % 4);
+    w4hi[idx] = hi; w4lo[idx] = wv - hi;
   }
   e->use_tensor_cores = 1;
   Blob b;
@@ -94,7 +113,9 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   size_t o_f1w = b.add(W.fc1_w, F1 * LAT * 4), o_f1b = b.add(W.fc1_b, F1 * 4), o_f2w = b.add(W.fc2_w, F2 * F1 * 4), o_f2b = b.add(W.fc2_b, F2 * 4);
   size_t o_f3w = b.add(W.fc3_w, F3 * F2 * 4), o_f3b = b.add(W.fc3_b, F3 * 4), o_ow = b.add(W.out_w, F3 * 4), o_ob = b.add(W.out_b, 4);
   size_t o_w1 = b.add(W.conv1_w, C1 * 4 * 4), o_b1 = b.add(W.conv1_b, C1 * 4);
-  size_t o_w3hi = b.add(w3hi.data(), w3hi.size() * 4), o_w3lo = b.add(w3lo.data(), w3lo.size() * 4);
+  size_t o_w32hi = b.add(w32hi.data(), w32hi.size() * 4), o_w32lo = b.add(w32lo.data(), w32lo.size() * 4);
+  size_t o_w4hi = b.add(w4hi.data(), w4hi.size() * 4), o_w4lo = b.add(w4lo.data(), w4lo.size() * 4);
+  size_t o_w2hi = b.add(w2hi.data(), w2hi.size() * 4), o_w2lo = b.add(w2lo.data(), w2lo.size() * 4), o_cbase = b.add(cbase.data(), cbase.size() * 4);
   size_t o_tri = sp->n_dist_tri > 0 ? b.add(sp->dist_tri, sizeof(double) * 9 * sp->n_dist_tri) : 0;
   std::vector<double> tri_sph((size_t)4 * (sp->n_dist_tri > 0 ? sp->n_dist_tri : 0));
   for (int t = 0; t < sp->n_dist_tri; t++) {
@@ -133,7 +154,8 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   c.b3 = FP(o_b3); c.w4 = FP(o_w4); c.b4 = FP(o_b4); c.fc1_w = FP(o_f1w); c.fc1_b = FP(o_f1b); c.fc2_w = FP(o_f2w);
   c.fc2_b = FP(o_f2b); c.fc3_w = FP(o_f3w); c.fc3_b = FP(o_f3b); c.out_w = FP(o_ow); c.out_b = FP(o_ob);
   c.w1 = FP(o_w1); c.b1 = FP(o_b1);
-  e->w3a_hi = FP(o_w3hi); e->w3a_lo = FP(o_w3lo);
+  e->tcw.w32_hi = FP(o_w32hi); e->tcw.w32_lo = FP(o_w32lo); e->tcw.w4_hi = FP(o_w4hi); e->tcw.w4_lo = FP(o_w4lo);
+  e->tcw.w2_hi = FP(o_w2hi); e->tcw.w2_lo = FP(o_w2lo); e->tcw.cbase = FP(o_cbase);
 #undef FP
   c.n_cloud = P_CLOUD; c.n_crop = sp->n_crop; c.n_dist_box = sp->n_dist_box; c.n_dist_tri = sp->n_dist_tri;
   memcpy(c.crop, sp->crop, sizeof(c.crop));

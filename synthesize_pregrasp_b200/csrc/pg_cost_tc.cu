@@ -1,57 +1,53 @@
-// Kernel 2 (tensor-core version): fused per-step cost with the dominant contraction on tcgen05.
+// Kernel 2 (tensor-core version): fused per-step cost, every convolution of the point network on tcgen05.
 //
-// Same algebra and interface as pcn_kernel<true> in pg_cost.cu (see its header for the reference citations).
-// Split of the work per 128-point tile of one evaluation:
-//   CUDA cores : conv1 (precomputed xyz part + df), conv2 32->64 (weights as constant-memory operands),
-//                +c / ReLU / conv4 256->20 on the accumulator rows read back from TMEM, masked max-pools
-//   tcgen05    : conv3 point half  D[128x256] = h2[128x64] x W3a^T[64x256], kind::tf32, fp32 accumulate in TMEM.
+// Same interface and geometry stage as pcn_kernel<true> in pg_cost.cu (see its header for the reference citations:
+// envs/plate_contact_graph_env.py:393-437 crop / distance field / projection, neurals/network.py:398-412 PCN).
+// Algebra per 128-point tile of one evaluation (exact identities, conv2 has no activation -- network.py:402-404):
+//   h1  = relu(conv1)                                   CUDA cores (4 -> 32: xyz part precomputed per point, + w1d * df)
+//   D2  = h1 . W2^T                 [128x32].[32x64]    tcgen05   -> global max-pool g (pass 1 over the cloud)
+//   D3  = h1 . (W3a W2)^T           [128x32].[32x256]   tcgen05   conv3's point half with conv2 folded in:  W3a (W2 h1 + b2)
+//   z   = relu(D3 + c),  c = b3 + W3a b2 + W3b g        epilogue on the TMEM rows; z is written straight back to shared
+//                                                       memory as the A operand of the next GEMM (back-to-back fusion)
+//   D4  = z . W4^T                  [128x256].[256x32]  tcgen05   (20 outputs padded to N = 32), accumulated over 8 K-chunks
+//   lat = masked max over points of D4 + b4
+// so all of the network's point-wise FLOPs (the ones SURVEY 8(d) counts: 164.1 MFLOP per evaluation) run on the tensor cores;
+// the [K, P, 256] activations never leave the SM.
 // fp32 fidelity on tf32 tensor cores: both operands are split a = a_hi + a_lo (a_hi = cvt.rna.tf32, a_lo = a - a_hi
 // exactly) and three MMAs a_hi*b_hi + a_hi*b_lo + a_lo*b_hi accumulate into the same TMEM tile (dropped term
 // a_lo*b_lo <= 2^-22 relative), because MPPI weights exp(-5*100*dlogit) do not tolerate plain-tf32 logits.
 // Operands sit in shared memory in the no-swizzle K-major canonical layout ([k-chunk of 16 B][row][16 B]:
-// SBO = 128 B between 8-row groups, LBO = rows*16 B between the two 16-byte halves of one K=8 step).
+// SBO = 128 B between 8-row groups, LBO = rows*16 B between the two 16-byte halves of one K=8 step).  The weight operands
+// (hi / lo, already in that layout) are brought in once per CTA by TMA bulk copies (cp.async.bulk -> mbarrier).
 #include "pg_internal.h"
 #include "pg_cost_geom.cuh"
 
 namespace pg {
 
-#ifndef TC_THREADS
 #define TC_THREADS 256
-#endif
 #define TC_M 128
-#define TC_NS (TC_THREADS / TC_M)          // column groups: each thread owns one point row and 1/TC_NS of the channels
-#define TC_CH (C2 / TC_NS)                // conv2 channels per thread
-#define TC_COLS (C3 / TC_NS)              // accumulator columns per thread
-
+#define TC_KC 32                         // conv4 K-chunk: channels of z staged per back-to-back step
+#define TC_N4 32                         // conv4 outputs padded to a legal MMA N
 
 struct TcSmem {
-  float b_hi[C2 * C3];                 // W3a, tf32-rounded, canonical K-major: [(k/4)][n][k%4]
-  float b_lo[C2 * C3];
-  float a_buf[C2 * TC_M];              // h2 tile (hi part, then lo part): [(k/4)][row][k%4]; also the conv4 partial exchange
-  float w2t[C1 * C2];                  // conv2 [j][c]
-  float w4t[C3 * C4];                  // conv4 [ch][o]
-  float b2[C2], w1d[C1], b4[C4 + 4];
+  float w32_hi[C1 * C3], w32_lo[C1 * C3];   // (W3a W2)  [256 x 32]  canonical K-major: [(k/4)][n][k%4]
+  float w4_hi[C3 * TC_N4], w4_lo[C3 * TC_N4];   // W4 (padded) [32 x 256]
+  float w2_hi[C1 * C2], w2_lo[C1 * C2];     // W2        [64 x 32]
+  float a1_hi[C1 * TC_M], a1_lo[C1 * TC_M]; // h1 tile   [128 x 32]  [(k/4)][row][k%4]
+  float a4_hi[TC_KC * TC_M], a4_lo[TC_KC * TC_M];   // z chunk [128 x 32]
   float df[P_CLOUD];
   float c[C3];
   float g[C2];
+  float b2[C2], w1d[C1], b4[TC_N4];
   float red[8 * C2];
   float lat[LAT + 2];
   double pose[7], R[9], fin[6];
   unsigned char msk[P_CLOUD];
-  unsigned long long mbar;
+  unsigned long long mbar, mbar_w;
   unsigned int tmem_base;
   int count;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// two independent fp32 FMAs in one instruction (FFMA2): d = a * b + d, bit-identical to two fmaf
-__device__ __forceinline__ void ffma2(float2& d, float2 a, float2 b) {
-  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
-  const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a), bb = *reinterpret_cast<const unsigned long long*>(&b);
-  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
-  d = *reinterpret_cast<float2*>(&dd);
-}
 
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -69,9 +65,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;                            // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE (0)
 }
 
-// kind::tf32, fp32 accumulate, K-major A and B, M=128, N=256 (cute::UMMA::InstrDescriptor bit layout)
-__device__ __forceinline__ uint32_t make_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C3 >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// kind::tf32, fp32 accumulate, K-major A and B, M = 128, N = n (cute::UMMA::InstrDescriptor bit layout)
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -79,6 +75,26 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
       :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// D[128 x N] (+)= A[128 x K] . B[N x K]^T with the 3x-split: per K = 8 step  a_hi b_hi + a_hi b_lo + a_lo b_hi.
+// A: rows = TC_M, B: rows = N, both canonical K-major; issued by ONE thread.
+template <int N, int K>
+__device__ __forceinline__ void gemm_split3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t accumulate) {
+  const uint32_t lbo_a = TC_M * 16, lbo_b = N * 16, sbo = 128;
+  constexpr uint32_t idesc = make_idesc(N);
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ks++) {                               // K = 8 tf32 per instruction = 2 chunks of 16 B
+    const uint64_t ah = make_desc(a_hi + ks * 2 * lbo_a, lbo_a, sbo), al = make_desc(a_lo + ks * 2 * lbo_a, lbo_a, sbo);
+    const uint64_t bh = make_desc(b_hi + ks * 2 * lbo_b, lbo_b, sbo), bl = make_desc(b_lo + ks * 2 * lbo_b, lbo_b, sbo);
+    mma_tf32(tmem_d, ah, bh, idesc, (ks > 0 || accumulate) ? 1u : 0u);
+    mma_tf32(tmem_d, ah, bl, idesc, 1u);
+    mma_tf32(tmem_d, al, bh, idesc, 1u);
+  }
+}
+
+__device__ __forceinline__ void mma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
@@ -89,6 +105,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   } while (!done);
 }
 
+// TMA bulk copy global -> shared, completion on an mbarrier (bytes: multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+#define TC_LD16(v, taddr)                                                                                                       \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),     \
+                 "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                        \
+               : "r"(taddr))
+#define TC_LD_WAIT() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+
 __device__ __forceinline__ float tc_box_dist(double x, double y, double z, const double* lo, const double* hi) {
   double dx = fmax(fmax(lo[0] - x, x - hi[0]), 0.0), dy = fmax(fmax(lo[1] - y, y - hi[1]), 0.0),
          dz = fmax(fmax(lo[2] - z, z - hi[2]), 0.0);
@@ -97,95 +126,64 @@ __device__ __forceinline__ float tc_box_dist(double x, double y, double z, const
   return (float)(outside > 0 ? outside : fmax(inside, 0.0));
 }
 
-// conv1 + TC_CH of the 64 conv2 channels (group G selects which) for point p; weights broadcast from shared memory
-template <int G>
-__device__ __forceinline__ void point_h2_grp_t(const TcSmem& s, const CostDev& cd, int p, float df, float* out) {
-  float h1[C1];
-  const float4* a = reinterpret_cast<const float4*>(cd.a1 + (size_t)p * C1);
+// conv1 + ReLU for 16 of the 32 channels of point p (thread (row, grp): channels 16 grp ..), split into tf32 hi / lo and
+// stored as the A operand of the next GEMM; rows beyond the cloud are zero
+__device__ __forceinline__ void stage_h1(TcSmem& s, const CostDev& cd, int p, int P, int row, int grp) {
 #pragma unroll
-  for (int j = 0; j < C1 / 4; j++) {
-    float4 v = __ldg(a + j);
-    h1[4 * j + 0] = fmaxf(fmaf(s.w1d[4 * j + 0], df, v.x), 0.f);
-    h1[4 * j + 1] = fmaxf(fmaf(s.w1d[4 * j + 1], df, v.y), 0.f);
-    h1[4 * j + 2] = fmaxf(fmaf(s.w1d[4 * j + 2], df, v.z), 0.f);
-    h1[4 * j + 3] = fmaxf(fmaf(s.w1d[4 * j + 3], df, v.w), 0.f);
-  }
-#pragma unroll
-  for (int c = 0; c < TC_CH; c++) out[c] = s.b2[G * TC_CH + c];
-#pragma unroll
-  for (int j = 0; j < C1; j++) {
-    const float4* w = reinterpret_cast<const float4*>(s.w2t + j * C2 + G * TC_CH);
-#pragma unroll
-    const float2 hh = make_float2(h1[j], h1[j]);
-    for (int c4 = 0; c4 < TC_CH / 4; c4++) {
-      float4 wv = w[c4];
-      float2* o2 = reinterpret_cast<float2*>(out + 4 * c4);
-      ffma2(o2[0], make_float2(wv.x, wv.y), hh);
-      ffma2(o2[1], make_float2(wv.z, wv.w), hh);
+  for (int q = 0; q < 4; q++) {
+    const int j = 16 * grp + 4 * q;
+    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+    if (p < P) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(cd.a1 + (size_t)p * C1 + j));
+      const float df = s.df[p];
+      const float h0 = fmaxf(fmaf(s.w1d[j], df, v.x), 0.f), h1 = fmaxf(fmaf(s.w1d[j + 1], df, v.y), 0.f);
+      const float h2 = fmaxf(fmaf(s.w1d[j + 2], df, v.z), 0.f), h3 = fmaxf(fmaf(s.w1d[j + 3], df, v.w), 0.f);
+      hi = make_float4(tf32_rna(h0), tf32_rna(h1), tf32_rna(h2), tf32_rna(h3));
+      lo = make_float4(h0 - hi.x, h1 - hi.y, h2 - hi.z, h3 - hi.w);
     }
-  }
-}
-__device__ __forceinline__ void point_h2_grp(const TcSmem& s, const CostDev& cd, int p, float df, int grp, float* out) {   // grp is warp-uniform
-  switch (grp) {
-    case 0: point_h2_grp_t<0>(s, cd, p, df, out); break;
-    case 1: point_h2_grp_t<1>(s, cd, p, df, out); break;
-#if TC_NS > 2
-    case 2: point_h2_grp_t<2>(s, cd, p, df, out); break;
-    default: point_h2_grp_t<3>(s, cd, p, df, out); break;
-#else
-    default: break;
-#endif
-  }
-}
-// +c, ReLU and the conv4 partial sums of 32 accumulator columns [cbase, cbase+32)
-__device__ __forceinline__ void conv4_block(const TcSmem& s, int cbase, const uint32_t* v, float* out) {
-#pragma unroll
-  for (int j = 0; j < 32; j++) {
-    float h = fmaxf(__uint_as_float(v[j]) + s.c[cbase + j], 0.f);
-    const float4* w = reinterpret_cast<const float4*>(s.w4t + (cbase + j) * C4);
-#pragma unroll
-    const float2 hh = make_float2(h, h);
-    for (int o4 = 0; o4 < C4 / 4; o4++) {
-      float4 wv = w[o4];
-      float2* o2 = reinterpret_cast<float2*>(out + 4 * o4);
-      ffma2(o2[0], make_float2(wv.x, wv.y), hh);
-      ffma2(o2[1], make_float2(wv.z, wv.w), hh);
-    }
+    const int o = ((j >> 2) * TC_M + row) * 4;
+    *reinterpret_cast<float4*>(s.a1_hi + o) = hi;
+    *reinterpret_cast<float4*>(s.a1_lo + o) = lo;
   }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restrict__ w3a_lo,
-              const double* __restrict__ pose, const double* __restrict__ fins, int B, float* __restrict__ latent) {
+pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const double* __restrict__ fins, int B, float* __restrict__ latent) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid & (TC_M - 1), grp = tid >> 7;        // TMEM lane / point row of this thread, column group
+  const int row = tid & (TC_M - 1), grp = tid >> 7;        // TMEM lane / point row of this thread, column half
   const int P = cd.n_cloud;
+  const uint32_t mbar = smem_u32(&s.mbar), mbar_w = smem_u32(&s.mbar_w);
 
-  // ---- one-time setup: weights into shared memory (W3a in the canonical layout), TMEM allocation, mbarrier
-  for (int i = tid; i < C2 * C3; i += TC_THREADS) { s.b_hi[i] = w3a_hi[i]; s.b_lo[i] = w3a_lo[i]; }
-  for (int i = tid; i < C1 * C2; i += TC_THREADS) s.w2t[i] = cd.w2t[i];
-  for (int i = tid; i < C3 * C4; i += TC_THREADS) { int ch = i / C4, o = i % C4; s.w4t[i] = cd.w4[o * C3 + ch]; }
-  if (tid < C2) s.b2[tid] = cd.b2[tid];
-  if (tid < C1) s.w1d[tid] = cd.w1d[tid];
-  if (tid < C4) s.b4[tid] = cd.b4[tid];
+  // ---- one-time setup: TMEM allocation, mbarriers, weight operands by TMA bulk copies
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s.tmem_base)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s.tmem_base)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s.mbar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_w));
     asm volatile("fence.mbarrier_init.release.cluster;");
+    const uint32_t bytes = 4u * (2 * C1 * C3 + 2 * C3 * TC_N4 + 2 * C1 * C2);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_w), "r"(bytes) : "memory");
+    bulk_g2s(s.w32_hi, tw.w32_hi, 4u * C1 * C3, mbar_w); bulk_g2s(s.w32_lo, tw.w32_lo, 4u * C1 * C3, mbar_w);
+    bulk_g2s(s.w4_hi, tw.w4_hi, 4u * C3 * TC_N4, mbar_w); bulk_g2s(s.w4_lo, tw.w4_lo, 4u * C3 * TC_N4, mbar_w);
+    bulk_g2s(s.w2_hi, tw.w2_hi, 4u * C1 * C2, mbar_w); bulk_g2s(s.w2_lo, tw.w2_lo, 4u * C1 * C2, mbar_w);
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid < C2) s.b2[tid] = cd.b2[tid];
+  if (tid < C1) s.w1d[tid] = cd.w1d[tid];
+  if (tid < TC_N4) s.b4[tid] = tid < C4 ? cd.b4[tid] : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
-  const uint32_t tmem_d = s.tmem_base;
-  const uint32_t idesc = make_idesc();
-  const uint32_t a_addr = smem_u32(s.a_buf), b_hi_addr = smem_u32(s.b_hi), b_lo_addr = smem_u32(s.b_lo);
-  const uint32_t mbar = smem_u32(&s.mbar);
+  mbar_wait(mbar_w, 0);                                    // weights landed (async proxy writes, visible to the tensor core)
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t tm_d3 = tmem, tm_d4 = tmem + C3, tm_d2 = tmem;          // D3: columns 0..255, D4: 256..287, D2 (pass 1) aliases D3
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t a1h = smem_u32(s.a1_hi), a1l = smem_u32(s.a1_lo), a4h = smem_u32(s.a4_hi), a4l = smem_u32(s.a4_lo);
+  const uint32_t w32h = smem_u32(s.w32_hi), w32l = smem_u32(s.w32_lo), w4h = smem_u32(s.w4_hi), w4l = smem_u32(s.w4_lo);
+  const uint32_t w2h = smem_u32(s.w2_hi), w2l = smem_u32(s.w2_lo);
   uint32_t phase = 0;
 
   for (int e = blockIdx.x; e < B; e += gridDim.x) {
@@ -259,41 +257,12 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
       }
       __syncthreads();
     }
-    // ---------------- stage 1: g = masked max over points of conv2 (this thread: 32 channels of its rows)
-    float gmax[TC_CH];
-#pragma unroll
-    for (int c = 0; c < TC_CH; c++) gmax[c] = -INFINITY;
-    for (int t0 = 0; t0 < P; t0 += TC_M) {
-      int p = t0 + row;
-      if (p < P && s.msk[p]) {
-        float h2[TC_CH];
-        point_h2_grp(s, cd, p, s.df[p], grp, h2);
-#pragma unroll
-        for (int c = 0; c < TC_CH; c++) gmax[c] = fmaxf(gmax[c], h2[c]);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < TC_CH; c++) {
-      float v = gmax[c];
-      for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-      gmax[c] = v;
-    }
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) reinterpret_cast<int*>(s.red)[warp] = cnt;
     __syncthreads();
-    if (lane == 0) {
-      for (int c = 0; c < TC_CH; c++) s.red[warp * TC_CH + c] = gmax[c];     // the four warps of group g hold channels g*TC_CH ..
-      reinterpret_cast<int*>(s.red + 8 * 32)[warp] = cnt;
-    }
-    __syncthreads();
-    if (tid < C2) {
-      int h = tid / TC_CH, c = tid % TC_CH;
-      float v = s.red[(4 * h) * TC_CH + c];
-      for (int w = 1; w < 4; w++) v = fmaxf(v, s.red[(4 * h + w) * TC_CH + c]);
-      s.g[tid] = v;
-    }
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < TC_THREADS / 32; w++) t += reinterpret_cast<int*>(s.red + 8 * 32)[w];
+      for (int w = 0; w < TC_THREADS / 32; w++) t += reinterpret_cast<int*>(s.red)[w];
       s.count = t;
     }
     __syncthreads();
@@ -302,121 +271,141 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
       __syncthreads();
       continue;
     }
-    if (tid < C3) {
-      float v = cd.b3[tid];
+
+    // ---------------- pass 1: g = masked max over points of conv2 (tcgen05, N = 64); thread (row, grp): channels 32 grp ..
+    float gmax[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) gmax[c] = -INFINITY;
+    for (int t0 = 0; t0 < P; t0 += TC_M) {
+      const int p = t0 + row;
+      stage_h1(s, cd, p, P, row, grp);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncthreads();                                               // (also: every thread has finished reading D2 of the previous tile)
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        gemm_split3<C2, C1>(tm_d2, a1h, a1l, w2h, w2l, 0u);
+        mma_commit(mbar);
+      }
+      mbar_wait(mbar, phase); phase ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const bool keep = p < P && s.msk[p];
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint32_t v[16];
+        TC_LD16(v, tm_d2 + lane_base + (uint32_t)(32 * grp + 16 * half));
+        TC_LD_WAIT();
+        if (keep) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) gmax[16 * half + i] = fmaxf(gmax[16 * half + i], __uint_as_float(v[i]) + s.b2[32 * grp + 16 * half + i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      float v = gmax[c];
+      for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+      gmax[c] = v;
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 32; c++) s.red[warp * 32 + c] = gmax[c];   // the four warps of half `grp` hold channels 32 grp ..
+    }
+    __syncthreads();
+    if (tid < C2) {
+      const int h = tid / 32, c = tid % 32;
+      float v = s.red[(4 * h) * 32 + c];
+      for (int w = 1; w < 4; w++) v = fmaxf(v, s.red[(4 * h + w) * 32 + c]);
+      s.g[tid] = v;
+    }
+    __syncthreads();
+    if (tid < C3) {                                                  // c = (b3 + W3a b2) + W3b g
+      float v = tw.cbase[tid];
       for (int k = 0; k < C2; k++) v = fmaf(__ldg(cd.w3bt + k * C3 + tid), s.g[k], v);
       s.c[tid] = v;
     }
     __syncthreads();
 
-    // ---------------- stage 2: per 128-point tile: conv2 -> tcgen05 conv3 -> (+c, relu, conv4) -> masked max
-    float rmax[C4];
+    // ---------------- pass 2: per 128-point tile  h1 -> [tcgen05 D3] -> z chunks -> [tcgen05 D4] -> masked max
+    float rmax[16];                                                  // thread (row, grp): conv4 outputs 16 grp .. (outputs >= 20 are padding)
 #pragma unroll
-    for (int o = 0; o < C4; o++) rmax[o] = -INFINITY;
+    for (int o = 0; o < 16; o++) rmax[o] = -INFINITY;
     for (int t0 = 0; t0 < P; t0 += TC_M) {
       const int p = t0 + row;
-      {
-        float h2[TC_CH];
-        if (p < P) point_h2_grp(s, cd, p, s.df[p], grp, h2);
-        else {
+      stage_h1(s, cd, p, P, row, grp);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncthreads();                                               // (also: D3 / D4 of the previous tile have been read by everyone)
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        gemm_split3<C3, C1>(tm_d3, a1h, a1l, w32h, w32l, 0u);
+        mma_commit(mbar);
+      }
+      mbar_wait(mbar, phase); phase ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      // back-to-back: z chunk ch (channels 32 ch ..) = relu(D3 + c) -> shared memory (tf32 hi / lo) -> D4 += z_chunk . W4_chunk^T.
+      // The TMEM read and the arithmetic of chunk ch + 1 run while the tensor core works on chunk ch; only the stores wait.
+#pragma unroll 1
+      for (int ch = 0; ch < C3 / TC_KC; ch++) {
+        uint32_t v[16];
+        TC_LD16(v, tm_d3 + lane_base + (uint32_t)(TC_KC * ch + 16 * grp));
+        TC_LD_WAIT();
+        float4 hi[4], lo[4];
 #pragma unroll
-          for (int c = 0; c < TC_CH; c++) h2[c] = 0.f;
+        for (int q = 0; q < 4; q++) {
+          const float4 cc = *reinterpret_cast<const float4*>(s.c + TC_KC * ch + 16 * grp + 4 * q);
+          const float z0 = fmaxf(__uint_as_float(v[4 * q]) + cc.x, 0.f), z1 = fmaxf(__uint_as_float(v[4 * q + 1]) + cc.y, 0.f);
+          const float z2 = fmaxf(__uint_as_float(v[4 * q + 2]) + cc.z, 0.f), z3 = fmaxf(__uint_as_float(v[4 * q + 3]) + cc.w, 0.f);
+          hi[q] = make_float4(tf32_rna(z0), tf32_rna(z1), tf32_rna(z2), tf32_rna(z3));
+          lo[q] = make_float4(z0 - hi[q].x, z1 - hi[q].y, z2 - hi[q].z, z3 - hi[q].w);
         }
-        // split a = hi + lo; hi goes to the operand buffer now, lo is kept in registers for the second phase
-        float lo[TC_CH];
+        if (ch > 0) { mbar_wait(mbar, phase); phase ^= 1; }         // the MMAs that read the previous chunk are done: the buffer is free
 #pragma unroll
-        for (int q = 0; q < TC_CH / 4; q++) {
-          float4 hi;
-          hi.x = tf32_rna(h2[4 * q]); hi.y = tf32_rna(h2[4 * q + 1]); hi.z = tf32_rna(h2[4 * q + 2]); hi.w = tf32_rna(h2[4 * q + 3]);
-          lo[4 * q] = h2[4 * q] - hi.x; lo[4 * q + 1] = h2[4 * q + 1] - hi.y; lo[4 * q + 2] = h2[4 * q + 2] - hi.z; lo[4 * q + 3] = h2[4 * q + 3] - hi.w;
-          *reinterpret_cast<float4*>(s.a_buf + ((grp * (TC_CH / 4) + q) * TC_M + row) * 4) = hi;
+        for (int q = 0; q < 4; q++) {
+          const int o = ((4 * grp + q) * TC_M + row) * 4;
+          *reinterpret_cast<float4*>(s.a4_hi + o) = hi[q];
+          *reinterpret_cast<float4*>(s.a4_lo + o) = lo[q];
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();
-        const uint32_t lbo_a = TC_M * 16, lbo_b = C3 * 16, sbo = 128;
-        if (tid == 0) {
-          asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll
-          for (int ks = 0; ks < C2 / 8; ks++) {                     // K = 8 tf32 per instruction = 2 chunks of 16 B
-            uint64_t ah = make_desc(a_addr + ks * 2 * lbo_a, lbo_a, sbo);
-            mma_tf32(tmem_d, ah, make_desc(b_hi_addr + ks * 2 * lbo_b, lbo_b, sbo), idesc, ks > 0 ? 1u : 0u);   // a_hi * b_hi
-            mma_tf32(tmem_d, ah, make_desc(b_lo_addr + ks * 2 * lbo_b, lbo_b, sbo), idesc, 1u);                 // a_hi * b_lo
-          }
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
-        }
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-        // second phase: the same buffer now carries a_lo
-#pragma unroll
-        for (int q = 0; q < TC_CH / 4; q++)
-          *reinterpret_cast<float4*>(s.a_buf + ((grp * (TC_CH / 4) + q) * TC_M + row) * 4) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();
         if (tid == 0) {
           asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll
-          for (int ks = 0; ks < C2 / 8; ks++)
-            mma_tf32(tmem_d, make_desc(a_addr + ks * 2 * lbo_a, lbo_a, sbo), make_desc(b_hi_addr + ks * 2 * lbo_b, lbo_b, sbo), idesc, 1u);  // a_lo * b_hi
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
-        }
-        mbar_wait(mbar, phase);
-        phase ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;");
-      }
-      // epilogue: this thread owns accumulator row `row`, columns grp*TC_COLS .. +TC_COLS
-      float out[C4];
-#pragma unroll
-      for (int o = 0; o < C4; o++) out[o] = 0.f;
-#pragma unroll
-      for (int cb = 0; cb < TC_COLS / 32; cb++) {
-        uint32_t v[32];
-        uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * TC_COLS + cb * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        conv4_block(s, grp * TC_COLS + cb * 32, v, out);
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;");
-      __syncthreads();                                             // all TMEM reads done; A buffers free
-      float* xch = s.a_buf;                                        // exchange the partial sums of groups 1..TC_NS-1
-      if (grp > 0) {
-#pragma unroll
-        for (int o = 0; o < C4; o++) xch[((grp - 1) * C4 + o) * TC_M + row] = out[o];
-      }
-      __syncthreads();
-      if (grp == 0) {
-        float m = (p < P && s.msk[p]) ? 0.f : -INFINITY;
-#pragma unroll
-        for (int o = 0; o < C4; o++) {
-          float acc = out[o];
-#pragma unroll
-          for (int gg = 0; gg < TC_NS - 1; gg++) acc += xch[(gg * C4 + o) * TC_M + row];
-          rmax[o] = fmaxf(rmax[o], acc + s.b4[o] + m);
+          // W4 chunk: K rows 32 ch .. of the [32 x 256] operand = byte offset (32 ch / 4) * (N * 16)
+          const uint32_t boff = (uint32_t)(TC_KC * ch / 4) * (TC_N4 * 16);
+          gemm_split3<TC_N4, TC_KC>(tm_d4, a4h, a4l, w4h + boff, w4l + boff, ch > 0 ? 1u : 0u);
+          mma_commit(mbar);
         }
       }
-      __syncthreads();
+      mbar_wait(mbar, phase); phase ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      {
+        uint32_t v[16];
+        TC_LD16(v, tm_d4 + lane_base + (uint32_t)(16 * grp));
+        TC_LD_WAIT();
+        const float m = (p < P && s.msk[p]) ? 0.f : -INFINITY;
+#pragma unroll
+        for (int o = 0; o < 16; o++) rmax[o] = fmaxf(rmax[o], __uint_as_float(v[o]) + s.b4[16 * grp + o] + m);
+      }
     }
-    // reduce rmax over the 128 rows (threads of half 0)
+    // reduce rmax over the 128 rows
 #pragma unroll
-    for (int o = 0; o < C4; o++) {
+    for (int o = 0; o < 16; o++) {
       float v = rmax[o];
       for (int k = 16; k > 0; k >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, k));
       rmax[o] = v;
     }
-    if (grp == 0 && lane == 0) for (int o = 0; o < C4; o++) s.red[warp * C4 + o] = rmax[o];
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < 16; o++) s.red[warp * 16 + o] = rmax[o];
+    }
     __syncthreads();
     if (tid < C4) {
-      float v = s.red[tid];
-      for (int w = 1; w < 4; w++) v = fmaxf(v, s.red[w * C4 + tid]);
+      const int h = tid / 16, o = tid % 16;
+      float v = s.red[(4 * h) * 16 + o];
+      for (int w = 1; w < 4; w++) v = fmaxf(v, s.red[(4 * h + w) * 16 + o]);
       s.lat[tid] = v;
     }
     __syncthreads();
@@ -425,7 +414,7 @@ pcn_tc_kernel(CostDev cd, const float* __restrict__ w3a_hi, const float* __restr
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(256));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -436,7 +425,7 @@ int launch_cost_tc(PgEnv* env, const double* pose, const double* fins, int B, fl
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->device);
   int grid = sms < B ? sms : B;
-  pcn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(env->cost, env->w3a_hi, env->w3a_lo, pose, fins, B, latent);
+  pcn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(env->cost, env->tcw, pose, fins, B, latent);
   count_launch();
   PG_CUDA(cudaGetLastError());
   return PG_OK;

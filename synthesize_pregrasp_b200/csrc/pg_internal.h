@@ -36,6 +36,14 @@ struct CostDev {                 // device pointers of the cost stage constants
   double clear_pos[2][3], clear_R[2][9], clear_size[3];
 };
 
+// tensor-core operands of the cost kernel: tf32 hi / lo splits in the UMMA canonical K-major layout [(k/4)][n][k%4]
+struct TcWeights {
+  const float *w32_hi, *w32_lo;  // (W3a W2): conv3's point half with conv2 folded in, [256 x 32]
+  const float *w4_hi, *w4_lo;    // conv4 padded to 32 outputs, [32 x 256]
+  const float *w2_hi, *w2_lo;    // conv2, [64 x 32]
+  const float* cbase;            // [256]  b3 + W3a b2
+};
+
 }  // namespace pg
 
 struct PgEnv {
@@ -44,7 +52,7 @@ struct PgEnv {
   pg::EnvDev* dev_env;
   pg::CostDev cost;
   void* blob;                    // one allocation holding every constant table
-  const float *w3a_hi, *w3a_lo;  // conv3 point-half weights, tf32 hi/lo split, UMMA canonical K-major layout
+  pg::TcWeights tcw;             // tensor-core operands of pcn_tc_kernel
   int use_tensor_cores;
   // scratch (grown on demand)
   double *pose, *fins;           // [K,N,7], [K,N,2,3]

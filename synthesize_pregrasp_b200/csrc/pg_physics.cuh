@@ -590,7 +590,11 @@ struct RowSet {
 // with the thread-local row records); host test build: a plain array
 #if defined(__CUDA_ARCH__)
 extern __shared__ double pg_solver_sm[];
+#if defined(PG_RUNTIME_STRIDE)
+#define PG_SM(i) pg_solver_sm[(i) * blockDim.x + threadIdx.x]      // slices strided by the launched CTA size: small launches keep the L1
+#else
 #define PG_SM(i) pg_solver_sm[(i) * PG_BLOCK_THREADS + threadIdx.x]
+#endif
 #else
 #define PG_SM(i) sm[(i) * ss]
 #endif

@@ -149,7 +149,8 @@ struct RolloutOut {
   int* settle_iters;  // optional [settle_substeps] (host diagnostics only)
   int sync_cta;       // device: every thread of this CTA runs a rollout in this pass (see substep)
   void* regroup;      // device: [K] RegroupSlot exchange buffer, or null (see settle_regroup)
-  int k;              // device: index of this rollout in the batch
+  int k;              // device: index of the rollout this thread currently runs
+  int k0;             // device: index of the CTA's first rollout in this pass (regroup exchanges stay inside [k0, k0 + blockDim.x))
 };
 
 // Settle-phase regrouping (device only).  The warp pays for its slowest lane: a rollout whose contact solver stops at the
@@ -163,6 +164,7 @@ struct RegroupSlot {
   double m0;
   double* pose;
   double* metric;
+  int k;
 };
 
 #if defined(__CUDA_ARCH__)
@@ -172,8 +174,8 @@ __device__ __noinline__ void settle_regroup(Sim& S, double& m0, RolloutOut& out,
   int* src = keys + blockDim.x;
   const int me = threadIdx.x, n = blockDim.x;
   __syncthreads();                                // every thread has left its last solve
-  RegroupSlot& mine = slots[out.k];
-  mine.S = S; mine.m0 = m0; mine.pose = out.pose; mine.metric = out.metric;
+  RegroupSlot& mine = slots[out.k0 + me];      // slot of this THREAD (the rollout it currently runs may come from an earlier re-deal)
+  mine.S = S; mine.m0 = m0; mine.pose = out.pose; mine.metric = out.metric; mine.k = out.k;
   keys[me] = key;
   __syncthreads();
   int rank = 0;
@@ -181,9 +183,9 @@ __device__ __noinline__ void settle_regroup(Sim& S, double& m0, RolloutOut& out,
   src[rank] = me;
   __syncthreads();
   const int from = src[me];
-  const RegroupSlot& theirs = slots[out.k - me + from];
+  const RegroupSlot& theirs = slots[out.k0 + from];
   S = theirs.S; m0 = theirs.m0; out.pose = theirs.pose; out.metric = theirs.metric;
-  out.k = out.k - me + from;
+  out.k = theirs.k;
   __syncthreads();                                // keys / src are overwritten by the next solve
 }
 #endif

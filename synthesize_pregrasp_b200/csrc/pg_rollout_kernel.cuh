@@ -7,6 +7,11 @@
 #ifndef PG_NO_SUBSTEP_BARRIER
 #define PG_SUBSTEP_BARRIER 1     // CTA barriers inside substep() (pg_physics.cuh): the warps of a CTA walk the collision code together
 #endif
+// settle phase: the CTA re-deals its rollouts to its threads again every PG_REGROUP_EVERY substeps (pg_rollout.cuh); measured on
+// bookshelf K = 65536: 1485-1519 ms without, 1416-1438 ms every 100, 1405-1424 ms every 50 (results bit-identical)
+#ifndef PG_REGROUP_EVERY
+#define PG_REGROUP_EVERY 50
+#endif
 #include <cstdlib>
 #include "pg_internal.h"
 #include "pg_rollout.cuh"
@@ -51,7 +56,7 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MINBLOCKS) rollout_kernel(const
     out.settle_iters = nullptr;
     out.sync_cta = cta_full;
     out.regroup = (cta_full && lanes == 32 && blockDim.x > 32) ? regroup : nullptr;
-    out.k = k;
+    out.k = k; out.k0 = k0;
     // several independent MPPI problems may share a launch: rollout k then uses the controls and the path of problem prob[k]
     const int q = prob ? prob[k] : 0;
     rollout_one<SHAPE>(*env, u + (size_t)q * N * ADIM, noise ? noise + (size_t)k * N * ADIM : nullptr, N, path + (size_t)q * N, max_force, 1, out, nullptr, 0);   // solver slice: dynamic shared memory, see PG_SM
@@ -82,7 +87,12 @@ static int launch_rollout_sized(cudaStream_t st, const EnvDev* env, const double
   if (wpc > max_warps) wpc = max_warps;
   int blocks = (warps + wpc - 1) / wpc;
   if (blocks > RK_MINBLOCKS * n_sm) blocks = RK_MINBLOCKS * n_sm;
-  rollout_kernel<SHAPE><<<blocks, 32 * wpc, smem, st>>>(env, u, noise, K, N, path, max_force, pose, fins, metric, trace, iters, prob, regroup, lanes);
+#if defined(PG_RUNTIME_STRIDE)
+  const size_t smem_launch = SM_DOUBLES * (size_t)(32 * wpc) * sizeof(double);
+#else
+  const size_t smem_launch = smem;
+#endif
+  rollout_kernel<SHAPE><<<blocks, 32 * wpc, smem_launch, st>>>(env, u, noise, K, N, path, max_force, pose, fins, metric, trace, iters, prob, regroup, lanes);
   return PG_OK;
 }
 

@@ -53,3 +53,26 @@ def oracle_cost_spec(spec):
 
 def oracle_weights():
     return dict(np.load(os.path.join(ROOT, "synthesize_pregrasp_b200", "assets", "score_with_df_2980.npz")))
+
+
+# ---- the PyBullet recordings the physics is pinned to (shared by the CPU oracle test and the GPU kernel test)
+PHYS = {  # exp: (rows to check, tolerance on pose) -- achieved tolerances, see DESIGN.md "Oracle / physics"
+    # With pybullet.multiplyTransforms emulated in float32 (oracle/envsim.py b3_multiply_transforms) the agreement is at rounding
+    # level up to the first discrete contact event the restatement does not reproduce (foodbox row 12, laptop row 7, keyboard 37)
+    "foodbox_20.0": (range(0, 12), 1e-12), "keyboard_20.0": (range(0, 24), 1e-12), "keyboard_scale_20.0": (range(0, 50), 2e-7),
+    "wall_laptop_20.0": (range(0, 7), 1e-12),
+    # both fingertips parked (and colliding with each other) in env step 1: per-island solves, exact; env step 2 with the
+    # floor friction the recording was made with (RECORDING_TIME below): a fingertip drags the 2 mm plate over the floor
+    "cardboard_20.0": (range(0, 66), 5e-8),
+    "plate_20.0": (range(0, 37), 1e-8),      # hull object: GJK + EPA narrowphase, compound pair rules
+    # URDF cylinder = 64-vertex prism hull; rows 3+: the floor's child manifold is created mid-run and must be solved after the
+    # fingertip's, which the pair-cache order delivers once the first (object, wall) pair precedes the fingertip pairs
+    "waterbottle_20.0": (range(0, 37), 5e-6),
+}
+
+
+# Env constants that changed in the reference AFTER a recording was made, identified from the recording itself: with the
+# committed cardboard env (floor lateralFriction 0.002, cardboard_contact_graph_env.py:193-194, under a "TODO: tune friction")
+# the first dragging substep is off by 1e-4; floor friction 0.005 reproduces the recorded displacement and rotation of that
+# substep to all printed digits and the following 15 substeps to 5e-8.  The product keeps the committed value.
+RECORDING_TIME = {"cardboard_20.0": {"floor_friction": 0.005}}

@@ -27,7 +27,7 @@ extern "C" int hostsim_rollout(const PgEnvSpec* sp, const double* u, const float
     out.trace = trace ? trace + (size_t)k * N * 50 * 7 : nullptr;
     out.iters = iters ? iters + (size_t)k * N * 50 : nullptr;
     out.settle_iters = g_settle ? g_settle + (size_t)k * 512 : nullptr;
-    out.sync_cta = 0; out.regroup = nullptr; out.k = k;
+    out.sync_cta = 0; out.regroup = nullptr; out.k = k; out.k0 = 0;
     double sm[pg::SM_DOUBLES];
     if (E.obj_shape != pg::SHAPE_BOX) pg::rollout_one<pg::SHAPE_HULL>(E, u, noise ? noise + (size_t)k * N * 48 : nullptr, N, path, max_force, train, out, sm, 1);
     else pg::rollout_one<pg::SHAPE_BOX>(E, u, noise ? noise + (size_t)k * N * 48 : nullptr, N, path, max_force, train, out, sm, 1);

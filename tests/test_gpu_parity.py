@@ -30,12 +30,25 @@ def _oracle_trace(spec, u, noise_row, F, train=False):
     return rs
 
 
+def _recording_time_spec(exp, env):
+    """The env as it was when `exp` was recorded (tests/test_oracle_cpu.py RECORDING_TIME: constants identified from the data)."""
+    import dataclasses
+    from helpers import RECORDING_TIME
+    from synthesize_pregrasp_b200.envspec import make_spec
+    spec = make_spec(env)
+    ff = RECORDING_TIME.get(exp, {}).get("floor_friction")
+    if ff is not None:
+        spec = dataclasses.replace(spec, statics=[dataclasses.replace(b, friction=ff) if b.name == "floor" else b for b in spec.statics])
+    return spec
+
+
 @pytest.mark.parametrize("exp", ["plate_20.0", "waterbottle_20.0", "foodbox_20.0", "keyboard_20.0", "keyboard_scale_20.0", "wall_laptop_20.0", "cardboard_20.0"])
 def test_physics_kernel_on_recorded_controls(EN, exp):
-    """K=1 replay of the reference's recorded u: kernel vs oracle (tight) and vs the PyBullet recording."""
-    from synthesize_pregrasp_b200.envspec import make_spec
+    """K=1 replay of the reference's recorded u: kernel vs oracle (tight) and vs the PyBullet recording over the SAME rows and
+    tolerances the oracle itself is held to (tests/test_oracle_cpu.py PHYS)."""
+    from helpers import PHYS
     g = recorded(exp)
-    spec = make_spec(g["env"])
+    spec = _recording_time_spec(exp, g["env"])
     eng = EN.RolloutEngine(spec, device=0)
     out = eng.physics(g["u"], None, [0, 0], g["max_force"], K=1, want_trace=True)
     tr = out["trace"][0].cpu().numpy()
@@ -43,8 +56,12 @@ def test_physics_kernel_on_recorded_controls(EN, exp):
     d = np.abs(tr - P).max(axis=1)
     assert d[:20].max() <= 1e-9, d[:20].max()              # same algorithm: rounding-level agreement early on
     assert np.median(d) <= 1e-7, np.median(d)
-    e = np.abs(tr - g["poses"]).max(axis=1)
-    assert e[0] <= 1e-6 and e[1] <= 1e-6, e[:2]            # first substeps reproduce PyBullet's recording
+    e = np.minimum(np.abs(tr - g["poses"]), np.abs(tr * np.r_[1, 1, 1, -1, -1, -1, -1] - g["poses"])).max(axis=1)   # q == -q
+    rows, tol = PHYS[exp]
+    # the kernel contracts a*b+c into FMAs (box objects) where PyBullet and the oracle round twice: rounding-level slack on top
+    assert e[0] <= 1e-11, e[0]
+    assert e[list(rows)].max() <= 4 * tol + 1e-10, (e[list(rows)].max(), tol)
+    print(f"{exp}: kernel vs PyBullet recording, rows {rows.start}-{rows.stop - 1}: max {e[list(rows)].max():.2e} (oracle bound {tol:.0e}); whole horizon {e.max():.2e}")
 
 
 @pytest.mark.parametrize("env,F", [("plate", 20.0), ("waterbottle", 20.0), ("foodbox", 20.0), ("bookshelf", 50.0), ("keyboard", 20.0)])
@@ -77,7 +94,7 @@ def test_physics_kernel_random_batch(EN, env, F):
     # measured agreement (160 rollouts on the GPU, 96 with the host build of the kernel code): 85-99 %, the toppling bottle
     # (403 substeps, polytope contacts) 73-79 %; required of these 48: 70 % and 55 %, so that the sample's own scatter
     # (binomial, sd ~2.5 rollouts) cannot fail the test
-    assert ok >= int((0.55 if env == "waterbottle" else 0.70) * K), ok
+    assert ok >= int({"waterbottle": 0.60, "bookshelf": 0.80}.get(env, 0.90) * K), ok
 
 
 @pytest.mark.parametrize("env", ["plate", "waterbottle", "foodbox", "bookshelf", "keyboard", "laptop", "cardboard"])
@@ -155,6 +172,78 @@ def test_end_to_end_cost_and_update_selection(EN):
     np.testing.assert_allclose(u_t.cpu().numpy(), un, rtol=0, atol=1e-12)
     assert abs(float(part[0]) - J.min()) == 0.0
     assert int(np.argmax(S)) == int(np.argmin(J))
+
+
+@pytest.mark.parametrize("env,F", [("plate", 20.0), ("bookshelf", 50.0)])
+def test_update_selection_kernel_vs_oracle(EN, env, F):
+    """north_star: "select the same MPPI update".  At the reference's own K = 12 x 30 = 360 samples (model_optimize.py:77) the
+    update computed from the KERNEL's costs is compared with the update computed from the ORACLE's costs on identical noise
+    (stoch_traj_opt.py:195-204): S = exp(-5 (J - min J)) is razor sharp, so one diverged low-cost rollout would own the update."""
+    from concurrent.futures import ProcessPoolExecutor
+    from oracle import mppi
+    from synthesize_pregrasp_b200.envspec import make_spec
+    spec = make_spec(env)
+    eng = EN.RolloutEngine(spec, device=0)
+    K, N = 360, 2
+    gen = torch.Generator(device="cuda:0").manual_seed(12367134)
+    noise = 0.8 * torch.randn((K, N, 48), generator=gen, device="cuda:0", dtype=torch.float32)
+    u = np.zeros((N, 48))
+    J = eng.rollout(u, noise, [0, 0], F).cpu().numpy()
+    nz = noise.cpu().numpy()
+    with ProcessPoolExecutor(min(16, os.cpu_count() or 1)) as ex:
+        Jr = np.array(list(ex.map(_oracle_J, [(env, F, nz[k]) for k in range(K)], chunksize=8)))
+    un_k, S_k = mppi.mppi_update(u, J, nz, 5.0, 1.0)
+    un_o, S_o = mppi.mppi_update(u, Jr, nz, 5.0, 1.0)
+    close = np.abs(J - Jr) <= 1e-3 * np.maximum(1.0, np.abs(Jr))
+    du = np.abs(un_k - un_o).max()
+    top_k, top_o = np.argsort(-S_k)[:5], np.argsort(-S_o)[:5]
+    print(f"{env}: K={K} costs within 1e-3 rel: {int(close.sum())}; arg-max weight kernel {top_k[0]} (S={S_k[top_k[0]]:.4f}) oracle {top_o[0]} "
+          f"(S={S_o[top_o[0]]:.4f}); top-5 kernel {top_k.tolist()} oracle {top_o.tolist()}; |du|_inf = {du:.3e}")
+    assert close.sum() >= int(0.85 * K)
+    assert top_k[0] == top_o[0], "the rollout that owns the update differs"
+    # the weights are exp(-5 dJ): a cost difference of 1e-3 (the fp32 network's rounding, x100) moves a weight by 0.5 %
+    assert du <= 2e-2, du
+
+
+def _oracle_J(args):
+    from oracle.rollout import rollout as oracle_rollout
+    from synthesize_pregrasp_b200.envspec import make_spec
+    env, F, nz = args
+    spec = make_spec(env)
+    return oracle_rollout(oracle_spec(spec), oracle_cost_spec(spec), oracle_weights(), np.zeros((2, 48)), nz, [0, 0, 0], F)["J"]
+
+
+@pytest.mark.parametrize("env,F", [("bookshelf", 50.0), ("foodbox", 20.0), ("plate", 20.0)])
+def test_device_kernel_matches_host_build_of_the_same_code(EN, env, F):
+    """Deterministic check of the DEVICE port: csrc/pg_rollout.cuh compiled for the host (tests/hostsim, no FMA contraction,
+    glibc math) against the CUDA build of the very same code, per control substep.  Differences can only come from FMA
+    contraction (box kernel) and libm (sin / cos / tanh / atan2), i.e. rounding level until a contact event amplifies them."""
+    import ctypes as C
+    import subprocess
+    from synthesize_pregrasp_b200 import _abi
+    from synthesize_pregrasp_b200.envspec import make_spec
+    so = os.path.join(ROOT, "tests", "hostsim", "libpg_hostsim.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-include", "cstdio", "-o", so,
+                           os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")])
+    H = C.CDLL(so)
+    spec = make_spec(env)
+    cs, keep = _abi.make_c_spec(spec)
+    K, N = 32, 2
+    gen = torch.Generator(device="cuda:0").manual_seed(77)
+    noise = 0.8 * torch.randn((K, N, 48), generator=gen, device="cuda:0", dtype=torch.float32)
+    u = np.zeros((N, 48))
+    out = EN.RolloutEngine(spec, device=0).physics(u, noise, [0, 0], F, want_trace=True)
+    tr_d = out["trace"].cpu().numpy().reshape(K, N * 50, 7)
+    nz = np.ascontiguousarray(noise.cpu().numpy())
+    pose = np.zeros((K, N, 7)); fins = np.zeros((K, N, 2, 3)); metric = np.zeros(K); trace = np.zeros((K, N * 50, 7)); path = np.zeros(N, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert H.hostsim_rollout(C.byref(cs), vp(u), vp(nz), K, N, vp(path), C.c_double(F), 1, vp(pose), vp(fins), vp(metric), vp(trace), None) == 0
+    d = np.abs(tr_d - trace).max(axis=2)                    # [K, 100] per control substep
+    assert np.array_equal(out["fins"].cpu().numpy(), fins)  # decode: bit-identical
+    assert d[:, :20].max() <= 1e-10, d[:, :20].max()        # every rollout, first 20 substeps: rounding level
+    whole = (d.max(axis=1) <= 1e-8).mean()
+    print(f"{env}: device vs host build, first 20 substeps max {d[:, :20].max():.1e}; {whole * 100:.0f} % of rollouts within 1e-8 over all 100 control substeps")
+    assert whole >= 0.6
 
 
 def test_mppi_update_kernel(EN):
