@@ -150,6 +150,23 @@ int pg_dyn_sweep_qp(const double* cloud_pts_dev, const double* cloud_nrm_dev, in
                     double tol, uint64_t first, uint64_t last, int32_t* triples_out_dev, uint64_t cap,
                     unsigned long long* count_dev, void* stream);
 
+/* Single-sample gym-style stepping: replaces env.reset() / env.step(a) of envs/<env>_contact_graph_env.py (plate_env:176-250,
+ * :253-632) for ONE episode advanced one env step per call.  PgCarry is the state an episode carries between env steps: the
+ * rigid-body world (bodies, persistent manifolds, servo constraints) and the decode carry (last_fins / last_surface_norm,
+ * plate_env:112-114, :137); it lives on the env's GPU.  All pointers are HOST pointers; the calls are synchronous.
+ *   pg_carry_create      a new episode in its post-reset state (runs reset())
+ *   pg_carry_reset       reset(); pose7_host (nullable) receives the object pose
+ *   pg_env_step_single   step(a): a_host [48] raw action (tanh is applied inside, :487); state = path[step_cnt] (:269-271);
+ *                        last_step != 0 runs the train-mode settle substeps and the metric (:556-603);
+ *                        reward = 100 x score logit (:611-612); trace_host [50,7] (nullable) = object pose at the start of each
+ *                        control substep (what model_test.py:124-135 records) */
+typedef struct PgCarry PgCarry;
+int pg_carry_create(PgEnv* env, PgCarry** out);
+int pg_carry_reset(PgCarry* carry, double* pose7_host);
+int pg_carry_destroy(PgCarry* carry);
+int pg_env_step_single(PgEnv* env, PgCarry* carry, const double* a_host, int32_t state, double max_force, int32_t last_step,
+                       double* reward_host, double* metric_host, double* pose7_host, double* trace_host);
+
 /* diagnostics: number of kernel launches issued through this library since load */
 uint64_t pg_launch_count(void);
 

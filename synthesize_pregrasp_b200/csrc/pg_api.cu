@@ -314,3 +314,78 @@ extern "C" int pg_rollout_host(PgEnv* e, const double* u_host, const float* nois
   PG_CUDA(cudaStreamSynchronize(st));
   return PG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-sample gym-style stepping (SURVEY 8(b) pg_env_step_single + PgCarry): one episode advanced one env step per call.
+struct PgCarry {
+  PgEnv* env;
+  void* state;          // pg::EpisodeState on the device
+  double* io;           // device staging: a[48] | pose[7] | fins[6] | metric[1] | trace[50*7]
+  float* logit;         // [1]
+  float* latent;        // [26]
+  int step;
+};
+enum { IO_A = 0, IO_POSE = ADIM, IO_FINS = ADIM + 7, IO_METRIC = ADIM + 13, IO_TRACE = ADIM + 14, IO_DOUBLES = ADIM + 14 + SKIP * 7 };
+
+extern "C" int pg_carry_reset(PgCarry* c, double* pose7_host) {
+  if (!c) { set_error("pg_carry_reset: null carry"); return PG_ERR_INVALID; }
+  PgEnv* e = c->env;
+  PG_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = e->host_stream;
+  int rc = launch_episode(e, c->state, nullptr, 0, 0.0, 0, c->io + IO_POSE, nullptr, nullptr, nullptr, st);
+  if (rc) return rc;
+  if (pose7_host) PG_CUDA(cudaMemcpyAsync(pose7_host, c->io + IO_POSE, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PG_CUDA(cudaStreamSynchronize(st));
+  c->step = 0;
+  return PG_OK;
+}
+
+extern "C" int pg_carry_create(PgEnv* e, PgCarry** out) {
+  if (!e || !out) { set_error("pg_carry_create: null argument"); return PG_ERR_INVALID; }
+  PG_CUDA(cudaSetDevice(e->device));
+  PgCarry* c = new PgCarry();
+  memset(c, 0, sizeof(PgCarry));
+  c->env = e;
+  cudaError_t ce = cudaMalloc(&c->state, episode_state_bytes());
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->io, IO_DOUBLES * sizeof(double));
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->logit, sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMalloc(&c->latent, LAT * sizeof(float));
+  if (ce != cudaSuccess) { cudaFree(c->state); cudaFree(c->io); cudaFree(c->logit); cudaFree(c->latent); delete c; return cuda_fail(ce, "cudaMalloc(carry)"); }
+  int rc = pg_carry_reset(c, nullptr);
+  if (rc) { cudaFree(c->state); cudaFree(c->io); cudaFree(c->logit); cudaFree(c->latent); delete c; return rc; }
+  *out = c;
+  return PG_OK;
+}
+
+extern "C" int pg_carry_destroy(PgCarry* c) {
+  if (!c) return PG_OK;
+  cudaSetDevice(c->env->device);
+  cudaFree(c->state); cudaFree(c->io); cudaFree(c->logit); cudaFree(c->latent);
+  delete c;
+  return PG_OK;
+}
+
+extern "C" int pg_env_step_single(PgEnv* e, PgCarry* c, const double* a_host, int32_t state, double max_force, int32_t last_step,
+                                  double* reward_host, double* metric_host, double* pose7_host, double* trace_host) {
+  if (!e || !c || c->env != e || !a_host) { set_error("pg_env_step_single: bad arguments"); return PG_ERR_INVALID; }
+  if (state < 0 || state >= e->host_env.n_states) { set_error("pg_env_step_single: contact state out of range"); return PG_ERR_INVALID; }
+  PG_CUDA(cudaSetDevice(e->device));
+  cudaStream_t st = e->host_stream;
+  PG_CUDA(cudaMemcpyAsync(c->io + IO_A, a_host, ADIM * sizeof(double), cudaMemcpyHostToDevice, st));
+  int rc = launch_episode(e, c->state, c->io + IO_A, state, max_force, last_step ? 1 : 0, c->io + IO_POSE, c->io + IO_FINS,
+                          c->io + IO_METRIC, trace_host ? c->io + IO_TRACE : nullptr, st);
+  if (rc) return rc;
+  // reward = 100 x score logit on the pose after this step (after the settle substeps on the last one), plate_env:608-612
+  rc = launch_cost(e, c->io + IO_POSE, c->io + IO_FINS, 1, c->latent, c->logit, st);
+  if (rc) return rc;
+  float logit = 0.f;
+  PG_CUDA(cudaMemcpyAsync(&logit, c->logit, sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (pose7_host) PG_CUDA(cudaMemcpyAsync(pose7_host, c->io + IO_POSE, 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (metric_host && last_step) PG_CUDA(cudaMemcpyAsync(metric_host, c->io + IO_METRIC, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (trace_host) PG_CUDA(cudaMemcpyAsync(trace_host, c->io + IO_TRACE, SKIP * 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PG_CUDA(cudaStreamSynchronize(st));
+  if (metric_host && !last_step) *metric_host = 0.0;
+  if (reward_host) *reward_host = 100.0 * (double)logit;
+  c->step += 1;
+  return PG_OK;
+}

@@ -42,7 +42,7 @@ struct TcSmem {
   float lat[LAT + 2];
   double pose[7], R[9], fin[6];
   unsigned char msk[P_CLOUD];
-  unsigned long long mbar, mbar_w;
+  unsigned long long mbar, mbar_w, mbar_b[2];
   unsigned int tmem_base;
   int count;
 };
@@ -78,18 +78,26 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
 }
 
 // D[128 x N] (+)= A[128 x K] . B[N x K]^T with the 3x-split: per K = 8 step  a_hi b_hi + a_hi b_lo + a_lo b_hi.
-// A: rows = TC_M, B: rows = N, both canonical K-major; issued by ONE thread.
+// A: rows = TC_M, B: rows = N, both canonical K-major; issued by ONE thread, which is the critical path of every step that
+// waits for the tensor core -- so the four operand descriptors are built ONCE (desc_* below) and a K step only advances their
+// 14-bit start-address field (address >> 4; the operands stay far below the field's 256 KB range, so the add never carries).
+struct OpDesc { uint64_t hi, lo; };                                   // descriptors of the hi / lo part of one operand at K step 0
+template <int ROWS>
+__device__ __forceinline__ OpDesc make_opdesc(uint32_t hi_addr, uint32_t lo_addr) {
+  OpDesc d;
+  d.hi = make_desc(hi_addr, ROWS * 16, 128);
+  d.lo = make_desc(lo_addr, ROWS * 16, 128);
+  return d;
+}
 template <int N, int K>
-__device__ __forceinline__ void gemm_split3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t accumulate) {
-  const uint32_t lbo_a = TC_M * 16, lbo_b = N * 16, sbo = 128;
+__device__ __forceinline__ void gemm_split3(uint32_t tmem_d, OpDesc a, OpDesc b, uint32_t accumulate) {
   constexpr uint32_t idesc = make_idesc(N);
+  constexpr uint64_t step_a = (2u * TC_M * 16u) >> 4, step_b = (2u * N * 16u) >> 4;   // one K = 8 step = two 16-byte chunks
 #pragma unroll
-  for (int ks = 0; ks < K / 8; ks++) {                               // K = 8 tf32 per instruction = 2 chunks of 16 B
-    const uint64_t ah = make_desc(a_hi + ks * 2 * lbo_a, lbo_a, sbo), al = make_desc(a_lo + ks * 2 * lbo_a, lbo_a, sbo);
-    const uint64_t bh = make_desc(b_hi + ks * 2 * lbo_b, lbo_b, sbo), bl = make_desc(b_lo + ks * 2 * lbo_b, lbo_b, sbo);
-    mma_tf32(tmem_d, ah, bh, idesc, (ks > 0 || accumulate) ? 1u : 0u);
-    mma_tf32(tmem_d, ah, bl, idesc, 1u);
-    mma_tf32(tmem_d, al, bh, idesc, 1u);
+  for (int ks = 0; ks < K / 8; ks++) {
+    mma_tf32(tmem_d, a.hi + ks * step_a, b.hi + ks * step_b, idesc, (ks > 0 || accumulate) ? 1u : 0u);
+    mma_tf32(tmem_d, a.hi + ks * step_a, b.lo + ks * step_b, idesc, 1u);
+    mma_tf32(tmem_d, a.lo + ks * step_a, b.hi + ks * step_b, idesc, 1u);
   }
 }
 
@@ -128,7 +136,7 @@ __device__ __forceinline__ float tc_box_dist(double x, double y, double z, const
 
 // conv1 + ReLU for 16 of the 32 channels of point p (thread (row, grp): channels 16 grp ..), split into tf32 hi / lo and
 // stored as the A operand of the next GEMM; rows beyond the cloud are zero
-__device__ __forceinline__ void stage_h1(TcSmem& s, const CostDev& cd, int p, int P, int row, int grp) {
+__device__ __forceinline__ void stage_h1(TcSmem& s, const CostDev& cd, int p, int P, int row, int grp, float* dst_hi, float* dst_lo) {
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     const int j = 16 * grp + 4 * q;
@@ -142,8 +150,8 @@ __device__ __forceinline__ void stage_h1(TcSmem& s, const CostDev& cd, int p, in
       lo = make_float4(h0 - hi.x, h1 - hi.y, h2 - hi.z, h3 - hi.w);
     }
     const int o = ((j >> 2) * TC_M + row) * 4;
-    *reinterpret_cast<float4*>(s.a1_hi + o) = hi;
-    *reinterpret_cast<float4*>(s.a1_lo + o) = lo;
+    *reinterpret_cast<float4*>(dst_hi + o) = hi;
+    *reinterpret_cast<float4*>(dst_lo + o) = lo;
   }
 }
 
@@ -164,6 +172,8 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_w));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s.mbar_b[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s.mbar_b[1])));
     asm volatile("fence.mbarrier_init.release.cluster;");
     const uint32_t bytes = 4u * (2 * C1 * C3 + 2 * C3 * TC_N4 + 2 * C1 * C2);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_w), "r"(bytes) : "memory");
@@ -181,10 +191,11 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
   const uint32_t tmem = s.tmem_base;
   const uint32_t tm_d3 = tmem, tm_d4 = tmem + C3, tm_d2 = tmem;          // D3: columns 0..255, D4: 256..287, D2 (pass 1) aliases D3
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  const uint32_t a1h = smem_u32(s.a1_hi), a1l = smem_u32(s.a1_lo), a4h = smem_u32(s.a4_hi), a4l = smem_u32(s.a4_lo);
-  const uint32_t w32h = smem_u32(s.w32_hi), w32l = smem_u32(s.w32_lo), w4h = smem_u32(s.w4_hi), w4l = smem_u32(s.w4_lo);
-  const uint32_t w2h = smem_u32(s.w2_hi), w2l = smem_u32(s.w2_lo);
-  uint32_t phase = 0;
+  const OpDesc d_a1 = make_opdesc<TC_M>(smem_u32(s.a1_hi), smem_u32(s.a1_lo)), d_a4 = make_opdesc<TC_M>(smem_u32(s.a4_hi), smem_u32(s.a4_lo));
+  const OpDesc d_w32 = make_opdesc<C3>(smem_u32(s.w32_hi), smem_u32(s.w32_lo)), d_w2 = make_opdesc<C2>(smem_u32(s.w2_hi), smem_u32(s.w2_lo));
+  const OpDesc d_w4 = make_opdesc<TC_N4>(smem_u32(s.w4_hi), smem_u32(s.w4_lo));
+  const uint32_t mbar_b0 = smem_u32(&s.mbar_b[0]), mbar_b1 = smem_u32(&s.mbar_b[1]);
+  uint32_t phase = 0, ph0 = 0, ph1 = 0;     // parities of mbar (D3 GEMM) and of the two operand-buffer barriers
 
   for (int e = blockIdx.x; e < B; e += gridDim.x) {
     // ---------------- stage 0: geometry (identical to pcn_kernel<true>)
@@ -276,28 +287,45 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
     float gmax[32];
 #pragma unroll
     for (int c = 0; c < 32; c++) gmax[c] = -INFINITY;
-    for (int t0 = 0; t0 < P; t0 += TC_M) {
-      const int p = t0 + row;
-      stage_h1(s, cd, p, P, row, grp);
+    // software pipeline over the tiles: two operand buffers (a1, a4) and two accumulator regions (D2[0], D2[1]); the tensor
+    // core works on tile t + 1 while the CUDA cores reduce tile t
+    {
+      const int T = (P + TC_M - 1) / TC_M;
+      stage_h1(s, cd, row, P, row, grp, s.a1_hi, s.a1_lo);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       asm volatile("tcgen05.fence::before_thread_sync;");
-      __syncthreads();                                               // (also: every thread has finished reading D2 of the previous tile)
+      __syncthreads();
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;");
-        gemm_split3<C2, C1>(tm_d2, a1h, a1l, w2h, w2l, 0u);
-        mma_commit(mbar);
+        gemm_split3<C2, C1>(tm_d2, d_a1, d_w2, 0u);
+        mma_commit(mbar_b0);
       }
-      mbar_wait(mbar, phase); phase ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      const bool keep = p < P && s.msk[p];
+      for (int t = 0; t < T; t++) {
+        const int b = t & 1;
+        if (t + 1 < T) {                                             // stage and launch tile t + 1 into the other buffer / region
+          stage_h1(s, cd, (t + 1) * TC_M + row, P, row, grp, b ? s.a1_hi : s.a4_hi, b ? s.a1_lo : s.a4_lo);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;");
+          __syncthreads();                                           // (also: everyone has read D2[1 - b] of tile t - 1)
+          if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            gemm_split3<C2, C1>(tm_d2 + (b ? 0u : (uint32_t)C2), b ? d_a1 : d_a4, d_w2, 0u);
+            mma_commit(b ? mbar_b0 : mbar_b1);
+          }
+        }
+        if (b) { mbar_wait(mbar_b1, ph1); ph1 ^= 1; } else { mbar_wait(mbar_b0, ph0); ph0 ^= 1; }
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const int p = t * TC_M + row;
+        const bool keep = p < P && s.msk[p];
 #pragma unroll
-      for (int half = 0; half < 2; half++) {
-        uint32_t v[16];
-        TC_LD16(v, tm_d2 + lane_base + (uint32_t)(32 * grp + 16 * half));
-        TC_LD_WAIT();
-        if (keep) {
+        for (int half = 0; half < 2; half++) {
+          uint32_t v[16];
+          TC_LD16(v, tm_d2 + (uint32_t)(b * C2) + lane_base + (uint32_t)(32 * grp + 16 * half));
+          TC_LD_WAIT();
+          if (keep) {
 #pragma unroll
-          for (int i = 0; i < 16; i++) gmax[16 * half + i] = fmaxf(gmax[16 * half + i], __uint_as_float(v[i]) + s.b2[32 * grp + 16 * half + i]);
+            for (int i = 0; i < 16; i++) gmax[16 * half + i] = fmaxf(gmax[16 * half + i], __uint_as_float(v[i]) + s.b2[32 * grp + 16 * half + i]);
+          }
         }
       }
     }
@@ -320,8 +348,12 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
     }
     __syncthreads();
     if (tid < C3) {                                                  // c = (b3 + W3a b2) + W3b g
+      float wk[C2];                                                  // all 64 loads in flight at once (they were a dependent L2-latency chain)
+#pragma unroll
+      for (int k = 0; k < C2; k++) wk[k] = __ldg(cd.w3bt + k * C3 + tid);
       float v = tw.cbase[tid];
-      for (int k = 0; k < C2; k++) v = fmaf(__ldg(cd.w3bt + k * C3 + tid), s.g[k], v);
+#pragma unroll
+      for (int k = 0; k < C2; k++) v = fmaf(wk[k], s.g[k], v);
       s.c[tid] = v;
     }
     __syncthreads();
@@ -332,21 +364,23 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
     for (int o = 0; o < 16; o++) rmax[o] = -INFINITY;
     for (int t0 = 0; t0 < P; t0 += TC_M) {
       const int p = t0 + row;
-      stage_h1(s, cd, p, P, row, grp);
+      stage_h1(s, cd, p, P, row, grp, s.a1_hi, s.a1_lo);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncthreads();                                               // (also: D3 / D4 of the previous tile have been read by everyone)
       if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;");
-        gemm_split3<C3, C1>(tm_d3, a1h, a1l, w32h, w32l, 0u);
+        gemm_split3<C3, C1>(tm_d3, d_a1, d_w32, 0u);
         mma_commit(mbar);
       }
       mbar_wait(mbar, phase); phase ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;");
       // back-to-back: z chunk ch (channels 32 ch ..) = relu(D3 + c) -> shared memory (tf32 hi / lo) -> D4 += z_chunk . W4_chunk^T.
-      // The TMEM read and the arithmetic of chunk ch + 1 run while the tensor core works on chunk ch; only the stores wait.
+      // Two operand buffers (a4, and a1 -- free once D3 is complete): the tensor core works on chunk ch while the CUDA cores
+      // prepare chunk ch + 1; a buffer is rewritten only after the MMAs of two chunks earlier have completed.
 #pragma unroll 1
       for (int ch = 0; ch < C3 / TC_KC; ch++) {
+        const int b = ch & 1;
         uint32_t v[16];
         TC_LD16(v, tm_d3 + lane_base + (uint32_t)(TC_KC * ch + 16 * grp));
         TC_LD_WAIT();
@@ -359,25 +393,29 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
           hi[q] = make_float4(tf32_rna(z0), tf32_rna(z1), tf32_rna(z2), tf32_rna(z3));
           lo[q] = make_float4(z0 - hi[q].x, z1 - hi[q].y, z2 - hi[q].z, z3 - hi[q].w);
         }
-        if (ch > 0) { mbar_wait(mbar, phase); phase ^= 1; }         // the MMAs that read the previous chunk are done: the buffer is free
+        if (ch >= 2) { if (b) { mbar_wait(mbar_b1, ph1); ph1 ^= 1; } else { mbar_wait(mbar_b0, ph0); ph0 ^= 1; } }
+        float* dh = b ? s.a1_hi : s.a4_hi;
+        float* dl = b ? s.a1_lo : s.a4_lo;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           const int o = ((4 * grp + q) * TC_M + row) * 4;
-          *reinterpret_cast<float4*>(s.a4_hi + o) = hi[q];
-          *reinterpret_cast<float4*>(s.a4_lo + o) = lo[q];
+          *reinterpret_cast<float4*>(dh + o) = hi[q];
+          *reinterpret_cast<float4*>(dl + o) = lo[q];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;");
         __syncthreads();
         if (tid == 0) {
           asm volatile("tcgen05.fence::after_thread_sync;");
-          // W4 chunk: K rows 32 ch .. of the [32 x 256] operand = byte offset (32 ch / 4) * (N * 16)
-          const uint32_t boff = (uint32_t)(TC_KC * ch / 4) * (TC_N4 * 16);
-          gemm_split3<TC_N4, TC_KC>(tm_d4, a4h, a4l, w4h + boff, w4l + boff, ch > 0 ? 1u : 0u);
-          mma_commit(mbar);
+          // W4 chunk: K rows 32 ch .. of the [32 x 256] operand = byte offset (32 ch / 4) * (N * 16), in descriptor units (>> 4)
+          const uint64_t boff = (uint64_t)((TC_KC * ch / 4) * (TC_N4 * 16) >> 4);
+          OpDesc w4c; w4c.hi = d_w4.hi + boff; w4c.lo = d_w4.lo + boff;
+          gemm_split3<TC_N4, TC_KC>(tm_d4, b ? d_a1 : d_a4, w4c, ch > 0 ? 1u : 0u);
+          mma_commit(b ? mbar_b1 : mbar_b0);
         }
       }
-      mbar_wait(mbar, phase); phase ^= 1;
+      mbar_wait(mbar_b0, ph0); ph0 ^= 1;                             // the last two chunks' MMAs
+      mbar_wait(mbar_b1, ph1); ph1 ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;");
       {
         uint32_t v[16];

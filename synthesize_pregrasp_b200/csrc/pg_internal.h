@@ -74,6 +74,9 @@ void count_launch();
 int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
                    double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st,
                    const int* prob_dev = nullptr);
+size_t episode_state_bytes();
+int launch_episode(PgEnv* env, void* state, const double* a, int cstate, double max_force, int settle, double* pose7, double* fins6,
+                   double* metric, double* trace, cudaStream_t st);
 int launch_cost(PgEnv* env, const double* pose, const double* fins, int B, float* latent, float* logit, cudaStream_t st);
 int launch_score(PgEnv* env, const float* pts, const float* df, const uint8_t* mask, const float* grasp, int B, int P,
                  float* latent, float* logit, cudaStream_t st);

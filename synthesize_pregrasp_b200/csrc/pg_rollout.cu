@@ -19,6 +19,23 @@ namespace pg {
 int launch_rollout_hull(cudaStream_t st, const EnvDev* env, const double* u, const float* noise, int K, int N, const int* path, double max_force,
                         double* pose, double* fins, double* metric, double* trace, int* iters, const int* prob, void* regroup);
 
+int launch_episode_hull(cudaStream_t st, const EnvDev* env, void* state, const double* a, int cstate, double max_force, int settle,
+                        double* pose7, double* fins6, double* metric, double* trace);
+
+size_t episode_state_bytes() { return sizeof(EpisodeState); }
+
+// one env step (or the reset, a == nullptr) of the single episode behind `state` (pg_env_step_single)
+int launch_episode(PgEnv* env, void* state, const double* a, int cstate, double max_force, int settle, double* pose7, double* fins6,
+                   double* metric, double* trace, cudaStream_t st) {
+  int rc;
+  if (env->host_env.obj_shape != SHAPE_BOX) rc = launch_episode_hull(st, env->dev_env, state, a, cstate, max_force, settle, pose7, fins6, metric, trace);
+  else rc = launch_episode_sized<SHAPE_BOX>(st, env->dev_env, state, a, cstate, max_force, settle, pose7, fins6, metric, trace);
+  if (rc) return rc;
+  count_launch();
+  PG_CUDA(cudaGetLastError());
+  return PG_OK;
+}
+
 int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
                    double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st, const int* prob_dev) {
   // exchange buffer of the settle-phase regrouping (pg_rollout.cuh), one slot per rollout

@@ -190,18 +190,9 @@ __device__ __noinline__ void settle_regroup(Sim& S, double& m0, RolloutOut& out,
 }
 #endif
 
-// sm / ss: the thread's on-chip solver slice (element i at sm[i*ss]); SM_DOUBLES elements
+// ---- reset(): plate_env:176-250.  Bodies at their spawn poses, tips parked at (f+2, f+2, f+2), one substep (:237).
 template <int SHAPE>
-PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, int N, const int* path,
-                        double max_force, int train, RolloutOut out, double* sm, int ss) {
-  Sim S;
-  RowSet rs;
-  M3 statR[MAX_STATICS];
-  for (int s = 0; s < E.n_static; s++) {
-    Q4 q; q.x = E.statics[s].quat[0]; q.y = E.statics[s].quat[1]; q.z = E.statics[s].quat[2]; q.w = E.statics[s].quat[3];
-    statR[s] = qmat(qnormalize(q));
-  }
-  // ---- reset(): plate_env:176-250
+PG_HD void env_reset(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, Carry& carry, int sync_cta, double* sm, int ss) {
   {
     DynBody& o = S.dyn[0];
     o.pos = V3(E.obj_pos[0], E.obj_pos[1], E.obj_pos[2]);
@@ -217,102 +208,127 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
       t.half = V3(E.tip_half[f][0], E.tip_half[f][1], E.tip_half[f][2]); t.friction = E.tip_friction;
     }
   }
-#if defined(PG_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
-  for (int i = 0; i < 6; i++) S.clk[i] = 0;
-  PG_CLK0(roll_t0);
-#endif
-  S.nman = 0; S.filter_off = 0; S.obj_first = 1; S.last_iterations = 0; S.early = 0; S.sync_cta = out.sync_cta;
+  S.nman = 0; S.filter_off = 0; S.obj_first = 1; S.last_iterations = 0; S.early = 0; S.sync_cta = sync_cta;
   for (int f = 0; f < 2; f++) { S.plo[f] = V3(); S.phi[f] = V3(); }
   S.cons[0].active = 0; S.cons[1].active = 0;
   substep<SHAPE>(E, S, statR, rs, sm, ss);                                                       // :237
   S.obj_first = 0;
-  Carry carry;
   for (int f = 0; f < NFING; f++) { carry.on[f] = 0; carry.pos[f] = V3(); carry.norm[f] = V3(); }
+}
 
+// ---- step(a): plate_env:253-632 for env step j of the episode (a = the raw action, before tanh).  `settle`: the train-mode
+// settle + metric of the last step (:556-603).  Writes out.fins / out.pose row j (+ trace / iters rows of this step).
+template <int SHAPE>
+PG_HD void env_step(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, Carry& carry, const double* a, int state, int prev_state,
+                    double max_force, bool settle, int j, RolloutOut& out, double* sm, int ss) {
+  V3 cur_pos[NFING];
+  int cur_on[NFING];
+  double knots[NFING][NKNOT][3];
+  decode_step(E, a, carry, state, prev_state, cur_pos, cur_on, knots);
+  // ---- pre_simulate :454-482
+  {
+    DynBody& o = S.dyn[0];
+    M3 R = qmat(o.q);
+    for (int i = 0; i < NFING; i++) {
+      V3 g = b3_multiply_transforms(o.pos, o.q, cur_pos[i]);       // float32, as pybullet.multiplyTransforms returns it
+      if (!check_clearance(E, g)) g = V3(100.0, 100.0, 100.0);
+      S.filter_off |= (1u << i);
+      refresh_proxy<SHAPE>(E, S, B_TIP0 + i);
+      refresh_proxy<SHAPE>(E, S, B_OBJ);
+      DynBody& t = S.dyn[1 + i];
+      t.pos = g; t.q = qnormalize(o.q); t.v = V3(); t.w = V3(); t.R = qmat(t.q);
+      S.cons[i].pivotB = g; S.cons[i].frameB = R; S.cons[i].max_impulse = E.default_max_impulse; S.cons[i].active = 1;
+    }
+    substep<SHAPE>(E, S, statR, rs, sm, ss);
+    for (int i = 0; i < NFING; i++) {
+      S.filter_off &= ~(1u << i);
+      refresh_proxy<SHAPE>(E, S, B_TIP0 + i);
+      refresh_proxy<SHAPE>(E, S, B_OBJ);
+    }
+  }
+  // ---- servo loop :504-533
+  int solver_work = 0;                            // regroup key: solver work of this control phase
+  for (int t = 0; t < SKIP; t++) {
+    DynBody& o = S.dyn[0];
+    if (out.trace) {
+      double* p = out.trace + (j * SKIP + t) * 7;
+      p[0] = o.pos.x; p[1] = o.pos.y; p[2] = o.pos.z; p[3] = o.q.x; p[4] = o.q.y; p[5] = o.q.z; p[6] = o.q.w;
+    }
+    M3 R = qmat(o.q);
+    V3 vel = o.v;
+    for (int i = 0; i < NFING; i++) {
+      V3 f(interp7(E, &knots[i][0][0], 3, t), interp7(E, &knots[i][0][1], 3, t), interp7(E, &knots[i][0][2], 3, t));
+      V3 v_g = b3_multiply_transforms(V3(), o.q, f) + vel * E.dt;       // the two transforms in float32 (pg_math.cuh), the sums in double
+      V3 tar = b3_multiply_transforms(o.pos, o.q, cur_pos[i]) + v_g;
+      S.cons[i].pivotB = tar; S.cons[i].frameB = R; S.cons[i].max_impulse = max_force * E.dt;
+    }
+    substep<SHAPE>(E, S, statR, rs, sm, ss);
+#if !defined(PG_PHASE_CLOCKS)
+    if (out.iters) out.iters[j * SKIP + t] = S.last_iterations;
+#endif
+#if defined(PG_REGROUP_EVERY)
+    solver_work += S.last_iterations * (12 + 2 * rs.n_pts);    // sweeps x rows
+#else
+    solver_work += S.last_iterations;
+#endif
+  }
+  for (int i = 0; i < NFING; i++) {
+    out.fins[(j * NFING + i) * 3 + 0] = cur_pos[i].x;
+    out.fins[(j * NFING + i) * 3 + 1] = cur_pos[i].y;
+    out.fins[(j * NFING + i) * 3 + 2] = cur_pos[i].z;
+  }
+  // ---- settle + metric :556-603 (train mode)
+  if (settle) {
+    double m0 = (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
+#if defined(__CUDA_ARCH__)
+    if (out.regroup) settle_regroup(S, m0, out, solver_work);     // from here on this thread may run another rollout of its CTA
+#endif
+#if defined(PG_REGROUP_EVERY)
+    int recent_work = 0;                              // solver work since the last re-deal
+#endif
+    for (int s = 0; s < E.settle_substeps; s++) {
+#if defined(__CUDA_ARCH__) && defined(PG_REGROUP_EVERY)
+      // the kind of a rollout drifts while it settles: re-deal again every PG_REGROUP_EVERY substeps by the work just seen
+      if (out.regroup && s > 0 && s % PG_REGROUP_EVERY == 0) { settle_regroup(S, m0, out, recent_work); recent_work = 0; }
+#endif
+      substep<SHAPE>(E, S, statR, rs, sm, ss);
+#if defined(PG_REGROUP_EVERY)
+      recent_work += S.last_iterations * (12 + 2 * rs.n_pts);
+#endif
+      if (out.settle_iters) out.settle_iters[s] = S.last_iterations;
+    }
+    if (out.metric) *out.metric = m0 + (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
+  }
+  DynBody& o = S.dyn[0];
+  double* p = out.pose + j * 7;
+  p[0] = o.pos.x; p[1] = o.pos.y; p[2] = o.pos.z; p[3] = o.q.x; p[4] = o.q.y; p[5] = o.q.z; p[6] = o.q.w;
+}
+
+PG_HD void static_rotations(const EnvDev& E, M3* statR) {
+  for (int s = 0; s < E.n_static; s++) {
+    Q4 q; q.x = E.statics[s].quat[0]; q.y = E.statics[s].quat[1]; q.z = E.statics[s].quat[2]; q.w = E.statics[s].quat[3];
+    statR[s] = qmat(qnormalize(q));
+  }
+}
+
+// sm / ss: the thread's on-chip solver slice (element i at sm[i*ss]); SM_DOUBLES elements
+template <int SHAPE>
+PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, int N, const int* path,
+                        double max_force, int train, RolloutOut out, double* sm, int ss) {
+  Sim S;
+  RowSet rs;
+  M3 statR[MAX_STATICS];
+  static_rotations(E, statR);
+#if defined(PG_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+  for (int i = 0; i < 6; i++) S.clk[i] = 0;
+  PG_CLK0(roll_t0);
+#endif
+  Carry carry;
+  env_reset<SHAPE>(E, S, statR, rs, carry, out.sync_cta, sm, ss);
   for (int j = 0; j < N; j++) {
     double a[ADIM];
     for (int d = 0; d < ADIM; d++) a[d] = u[j * ADIM + d] + (noise ? (double)noise[j * ADIM + d] : 0.0);
-    V3 cur_pos[NFING];
-    int cur_on[NFING];
-    double knots[NFING][NKNOT][3];
-    decode_step(E, a, carry, path[j], j == 0 ? -1 : path[j - 1], cur_pos, cur_on, knots);
-    // ---- pre_simulate :454-482
-    {
-      DynBody& o = S.dyn[0];
-      M3 R = qmat(o.q);
-      for (int i = 0; i < NFING; i++) {
-        V3 g = b3_multiply_transforms(o.pos, o.q, cur_pos[i]);       // float32, as pybullet.multiplyTransforms returns it
-        if (!check_clearance(E, g)) g = V3(100.0, 100.0, 100.0);
-        S.filter_off |= (1u << i);
-        refresh_proxy<SHAPE>(E, S, B_TIP0 + i);
-        refresh_proxy<SHAPE>(E, S, B_OBJ);
-        DynBody& t = S.dyn[1 + i];
-        t.pos = g; t.q = qnormalize(o.q); t.v = V3(); t.w = V3(); t.R = qmat(t.q);
-        S.cons[i].pivotB = g; S.cons[i].frameB = R; S.cons[i].max_impulse = E.default_max_impulse; S.cons[i].active = 1;
-      }
-      substep<SHAPE>(E, S, statR, rs, sm, ss);
-      for (int i = 0; i < NFING; i++) {
-        S.filter_off &= ~(1u << i);
-        refresh_proxy<SHAPE>(E, S, B_TIP0 + i);
-        refresh_proxy<SHAPE>(E, S, B_OBJ);
-      }
-    }
-    // ---- servo loop :504-533
-    int solver_work = 0;                            // regroup key: solver sweeps of this control phase
-    for (int t = 0; t < SKIP; t++) {
-      DynBody& o = S.dyn[0];
-      if (out.trace) {
-        double* p = out.trace + (j * SKIP + t) * 7;
-        p[0] = o.pos.x; p[1] = o.pos.y; p[2] = o.pos.z; p[3] = o.q.x; p[4] = o.q.y; p[5] = o.q.z; p[6] = o.q.w;
-      }
-      M3 R = qmat(o.q);
-      V3 vel = o.v;
-      for (int i = 0; i < NFING; i++) {
-        V3 f(interp7(E, &knots[i][0][0], 3, t), interp7(E, &knots[i][0][1], 3, t), interp7(E, &knots[i][0][2], 3, t));
-        V3 v_g = b3_multiply_transforms(V3(), o.q, f) + vel * E.dt;       // the two transforms in float32 (pg_math.cuh), the sums in double
-        V3 tar = b3_multiply_transforms(o.pos, o.q, cur_pos[i]) + v_g;
-        S.cons[i].pivotB = tar; S.cons[i].frameB = R; S.cons[i].max_impulse = max_force * E.dt;
-      }
-      substep<SHAPE>(E, S, statR, rs, sm, ss);
-#if !defined(PG_PHASE_CLOCKS)
-      if (out.iters) out.iters[j * SKIP + t] = S.last_iterations;
-#endif
-#if defined(PG_REGROUP_EVERY)
-      solver_work += S.last_iterations * (12 + 2 * rs.n_pts);    // sweeps x rows
-#else
-      solver_work += S.last_iterations;
-#endif
-    }
-    for (int i = 0; i < NFING; i++) {
-      out.fins[(j * NFING + i) * 3 + 0] = cur_pos[i].x;
-      out.fins[(j * NFING + i) * 3 + 1] = cur_pos[i].y;
-      out.fins[(j * NFING + i) * 3 + 2] = cur_pos[i].z;
-    }
-    // ---- settle + metric :556-603 (train mode)
-    if (j == N - 1 && train) {
-      double m0 = (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
-#if defined(__CUDA_ARCH__)
-      if (out.regroup) settle_regroup(S, m0, out, solver_work);     // from here on this thread may run another rollout of its CTA
-#endif
-#if defined(PG_REGROUP_EVERY)
-      int recent_work = 0;                              // solver work since the last re-deal
-#endif
-      for (int s = 0; s < E.settle_substeps; s++) {
-#if defined(__CUDA_ARCH__) && defined(PG_REGROUP_EVERY)
-        // the kind of a rollout drifts while it settles: re-deal again every PG_REGROUP_EVERY substeps by the work just seen
-        if (out.regroup && s > 0 && s % PG_REGROUP_EVERY == 0) { settle_regroup(S, m0, out, recent_work); recent_work = 0; }
-#endif
-        substep<SHAPE>(E, S, statR, rs, sm, ss);
-#if defined(PG_REGROUP_EVERY)
-        recent_work += S.last_iterations * (12 + 2 * rs.n_pts);
-#endif
-        if (out.settle_iters) out.settle_iters[s] = S.last_iterations;
-      }
-      if (out.metric) *out.metric = m0 + (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
-    }
-    DynBody& o = S.dyn[0];
-    double* p = out.pose + j * 7;
-    p[0] = o.pos.x; p[1] = o.pos.y; p[2] = o.pos.z; p[3] = o.q.x; p[4] = o.q.y; p[5] = o.q.z; p[6] = o.q.w;
+    env_step<SHAPE>(E, S, statR, rs, carry, a, path[j], j == 0 ? -1 : path[j - 1], max_force, j == N - 1 && train, j, out, sm, ss);
   }
 #if defined(PG_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
   // profiling builds: lane 0 of every warp adds its phase cycles to the counters behind out.iters (6 x unsigned long long)
@@ -324,5 +340,14 @@ PG_HDN void rollout_one(const EnvDev& E, const double* u, const float* noise, in
   }
 #endif
 }
+
+// The state one episode carries from env step to env step when it is advanced one step at a time (pg_env_step_single): the
+// rigid-body world (bodies, persistent manifolds, servo constraints, broadphase bookkeeping) and the decode carry
+// (last_fins / last_surface_norm, plate_env:112-114, :137).  Opaque to the ABI (PgCarry).
+struct EpisodeState {
+  Sim S;
+  Carry carry;
+  int step, prev_state;
+};
 
 }  // namespace pg

@@ -22,4 +22,9 @@ int launch_rollout_hull(cudaStream_t st, const EnvDev* env, const double* u, con
   return launch_rollout_sized<SHAPE_HULL>(st, env, u, noise, K, N, path, max_force, pose, fins, metric, trace, iters, prob, regroup);
 }
 
+int launch_episode_hull(cudaStream_t st, const EnvDev* env, void* state, const double* a, int cstate, double max_force, int settle,
+                        double* pose7, double* fins6, double* metric, double* trace) {
+  return launch_episode_sized<SHAPE_HULL>(st, env, state, a, cstate, max_force, settle, pose7, fins6, metric, trace);
+}
+
 }  // namespace pg

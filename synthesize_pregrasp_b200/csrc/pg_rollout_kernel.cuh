@@ -96,4 +96,55 @@ static int launch_rollout_sized(cudaStream_t st, const EnvDev* env, const double
   return PG_OK;
 }
 
+
+// One episode advanced ONE env step per launch (pg_env_step_single: the gym-style env.step of the reference, plate_env:253-632):
+// the state between steps lives in an EpisodeState in device memory.  a == nullptr: reset() (plate_env:176-250).
+// Same per-thread code as the batch kernel (env_reset / env_step), run by one thread.
+template <int SHAPE>
+__global__ void __launch_bounds__(32, 1) episode_kernel(const EnvDev* __restrict__ env, EpisodeState* __restrict__ st, const double* __restrict__ a,
+                                                        int state, double max_force, int settle, double* __restrict__ pose7,
+                                                        double* __restrict__ fins6, double* __restrict__ metric, double* __restrict__ trace) {
+  if (SHAPE == SHAPE_HULL) {
+    for (int i = threadIdx.x; i < 3 * env->n_hull; i += blockDim.x) pg_hull_sm[i] = env->hull[i];
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  RowSet rs;
+  M3 statR[MAX_STATICS];
+  static_rotations(*env, statR);
+  Sim S;
+  Carry carry;
+#if defined(PG_PHASE_CLOCKS)
+  for (int i = 0; i < 6; i++) S.clk[i] = 0;
+#endif
+  if (!a) {
+    env_reset<SHAPE>(*env, S, statR, rs, carry, 0, nullptr, 0);
+    st->step = 0; st->prev_state = -1;
+  } else {
+    S = st->S; carry = st->carry;
+    S.sync_cta = 0;
+    RolloutOut out;
+    out.pose = pose7; out.fins = fins6; out.metric = metric; out.trace = trace; out.iters = nullptr; out.settle_iters = nullptr;
+    out.sync_cta = 0; out.regroup = nullptr; out.k = 0; out.k0 = 0;
+    double act[ADIM];
+    for (int d = 0; d < ADIM; d++) act[d] = a[d];
+    env_step<SHAPE>(*env, S, statR, rs, carry, act, state, st->prev_state, max_force, settle != 0, 0, out, nullptr, 0);
+    st->step += 1; st->prev_state = state;
+  }
+  st->S = S; st->carry = carry;
+  if (!a && pose7) {
+    const DynBody& o = S.dyn[0];
+    pose7[0] = o.pos.x; pose7[1] = o.pos.y; pose7[2] = o.pos.z; pose7[3] = o.q.x; pose7[4] = o.q.y; pose7[5] = o.q.z; pose7[6] = o.q.w;
+  }
+}
+
+template <int SHAPE>
+static int launch_episode_sized(cudaStream_t st, const EnvDev* env, void* state, const double* a, int cstate, double max_force, int settle,
+                                double* pose7, double* fins6, double* metric, double* trace) {
+  const size_t smem = SM_DOUBLES * RK_THREADS * sizeof(double);       // the solver slices are strided by the compile-time CTA size
+  PG_CUDA(cudaFuncSetAttribute(episode_kernel<SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  episode_kernel<SHAPE><<<1, 32, smem, st>>>(env, (EpisodeState*)state, a, cstate, max_force, settle, pose7, fins6, metric, trace);
+  return PG_OK;
+}
+
 }  // namespace pg

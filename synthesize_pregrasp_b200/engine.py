@@ -179,6 +179,44 @@ class RolloutEngine:
         return logit
 
 
+class Episode:
+    """One episode advanced one env step per call (pg_env_step_single): the gym-style reset()/step() of the reference envs
+    (plate_contact_graph_env.py:176-250, :253-632).  The state between steps (PgCarry) stays on the GPU."""
+
+    def __init__(self, engine: RolloutEngine):
+        self.engine, self.lib = engine, engine.lib
+        h = C.c_void_p()
+        _abi.check(self.lib.pg_carry_create(engine.handle, C.byref(h)))
+        self.handle = h
+
+    def reset(self):
+        pose = np.zeros(7)
+        _abi.check(self.lib.pg_carry_reset(self.handle, pose.ctypes.data_as(_abi._DP)))
+        return pose
+
+    def step(self, a, state, max_force, last_step, want_trace=False):
+        """-> (reward, metric, pose[7], trace[50,7] or None)"""
+        a = np.ascontiguousarray(a, np.float64)
+        assert a.shape == (ACTION_DIM,)
+        reward, metric, pose = np.zeros(1), np.zeros(1), np.zeros(7)
+        trace = np.zeros((ES.CONTROL_SKIP, 7)) if want_trace else None
+        dp = lambda x: x.ctypes.data_as(_abi._DP) if x is not None else None
+        _abi.check(self.lib.pg_env_step_single(self.engine.handle, self.handle, dp(a), int(state), float(max_force), 1 if last_step else 0,
+                                               dp(reward), dp(metric), dp(pose), dp(trace)))
+        return float(reward[0]), float(metric[0]), pose, trace
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.pg_carry_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def mppi_update(J, noise, u, kappa=5.0, alpha=1.0, apply=True, want_partial=False):
     """Exp-weighted update on the device (stoch_traj_opt.py:195-204).  J [K] f64, noise [K,N,D] f32, u [N,D] f64
     CUDA tensors; u is updated in place when apply.  -> partial (min J, sum w, sum J, sum w*noise) if asked."""

@@ -1,7 +1,8 @@
 """gym-style shims with the constructor kwargs and reset()/step()/seed() surface of
 envs/*_contact_graph_env.py (plate_contact_graph_env.py:48-72, :176-250, :253-632, :657-659) that the
-optimiser and scripts rely on.  step() replays the action history through the batched kernel with K=1, so a
-single-sample caller sees the same numbers the MPPI batch does."""
+optimiser and scripts rely on.  step() is ONE pg_env_step_single call: the episode's state (rigid-body world, contact
+manifolds, decode carry) stays on the GPU between steps (PgCarry) and the step runs the very code the MPPI batch runs per
+rollout, so a single-sample caller sees the same numbers the batch does."""
 from __future__ import annotations
 
 import types
@@ -32,14 +33,15 @@ class _ContactGraphEnv:
         self.action_dim = ES.ACTION_DIM
         self.action_space = types.SimpleNamespace(shape=(self.action_dim,), low=-np.ones(self.action_dim),
                                                   high=np.ones(self.action_dim))
-        self._actions = []
+        self.episode = EN.Episode(self.engine)
+        self.step_cnt = 0
 
     def seed(self, seed=None):
         return [seed]
 
     def reset(self):
-        self._actions = []
-        return self._obs(np.r_[self.engine.spec.obj_pos, self.engine.spec.obj_quat])
+        self.step_cnt = 0
+        return self._obs(self.episode.reset())
 
     def _obs(self, pose):
         # get_extended_observation plate_env:634-655: 8 corners of a 0.4 x 0.4 x 0.1 box at the object pose
@@ -52,28 +54,12 @@ class _ContactGraphEnv:
         return list(((sg * dim) @ R.T + pose[:3]).ravel())
 
     def step(self, a, rollout_verify=False):
-        self._actions.append(np.asarray(a, np.float64))
-        n = len(self._actions)
-        if n > self.n_steps:
+        if self.step_cnt >= self.n_steps:
             raise RuntimeError("episode is over: call reset()")
-        u = np.stack(self._actions)
-        # costs accumulate per step: reward of this step = -(J_n - J_{n-1})
-        out = self.engine.physics(u, None, self.path, self.max_forces, K=1)
-        logit = self.engine.cost(out["pose"][0, n - 1:n], out["fins"][0, n - 1:n])
-        reward = 100.0 * float(logit.item())
-        done = n == self.n_steps
-        metric = 0.0
-        if done:
-            full = self.engine.rollout(u, None, self.path, self.max_forces, K=1, want_metric=True)
-            metric = float(full[1].item())
-            # the last step's reward is evaluated after the settle substeps (plate_env:556-612)
-            J = float(full[0].item())
-            prev = 0.0
-            for j in range(n - 1):
-                lj = self.engine.cost(out["pose"][0, j:j + 1], out["fins"][0, j:j + 1])
-                prev += -100.0 * float(lj.item())
-            reward = -(J - prev)
-        return self._obs(out["pose"][0, n - 1].cpu().numpy()), reward, done, {"metric": metric}
+        done = self.step_cnt == self.n_steps - 1                 # plate_env:556: the last step settles and reports the metric
+        reward, metric, pose, _ = self.episode.step(a, self.path[self.step_cnt], self.max_forces, last_step=done)
+        self.step_cnt += 1
+        return self._obs(pose), reward, done, {"metric": metric if done else 0.0}
 
 
 def _make(name, env_name):
