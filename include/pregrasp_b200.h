@@ -76,6 +76,11 @@ typedef struct PgEnvSpec {     /* the constructor kwargs + literals of envs/<env
   int32_t n_dist_box, n_dist_tri;
   double dist_box[4][2][3];    /* (min,max) corners of the distance-field boxes */
   const double* dist_tri;      /* [n_dist_tri,3,3] or NULL */
+  /* right prisms with a regular polygon cross-section, axis z: what Open3D's create_cylinder tessellates a cylinder into
+     (waterbottle holders, distancefield_utils.py:62-68).  Exactly the same surface as its triangle list, evaluated in closed
+     form: (cx, cy, cz, radius of the vertex circle, half height, number of sides <= 32); first vertex at angle 0 */
+  int32_t n_dist_prism, pad1;
+  double dist_prism[2][6];
   PgScoreWeights weights;
 } PgEnvSpec;
 

@@ -51,6 +51,7 @@ class PgEnvSpec(C.Structure):
         ("crop", ((C.c_double * 3) * 2) * 2),
         ("n_dist_box", C.c_int32), ("n_dist_tri", C.c_int32),
         ("dist_box", ((C.c_double * 3) * 2) * 4), ("dist_tri", _DP),
+        ("n_dist_prism", C.c_int32), ("pad1", C.c_int32), ("dist_prism", (C.c_double * 6) * 2),
         ("weights", PgScoreWeights),
     ]
 
@@ -136,7 +137,12 @@ def make_c_spec(spec: ES.EnvSpec, states=None, weights=None):
     for b in range(s.n_dist_box):
         for k in range(2):
             s.dist_box[b][k][:] = spec.dist_boxes[b][k]
-    if spec.dist_tris is not None:
+    if getattr(spec, "dist_prisms", None) is not None:          # closed form of the same polyhedra: the triangle list stays with the oracle
+        s.n_dist_prism = len(spec.dist_prisms)
+        for i, pr in enumerate(spec.dist_prisms):
+            for j in range(6):
+                s.dist_prism[i][j] = float(pr[j])
+    elif spec.dist_tris is not None:
         s.n_dist_tri = len(spec.dist_tris)
         s.dist_tri = dp(spec.dist_tris)
     weights = weights or load_score_weights()

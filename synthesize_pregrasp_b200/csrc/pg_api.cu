@@ -48,7 +48,8 @@ struct Blob {
 extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   if (!sp || !out) { set_error("pg_env_create: null argument"); return PG_ERR_INVALID; }
   if (sp->n_static < 1 || sp->n_static > MAX_STATICS || sp->n_regions > MAX_REGIONS || sp->n_states > MAX_STATES ||
-      sp->n_cloud != P_CLOUD || sp->n_crop < 1 || sp->n_crop > 2 || sp->n_dist_box < 0 || sp->n_dist_box > 4 || sp->n_dist_tri < 0 ||
+      sp->n_cloud != P_CLOUD || sp->n_crop < 1 || sp->n_crop > 2 || sp->n_dist_box < 0 || sp->n_dist_box > 4 || sp->n_dist_tri < 0 || sp->n_dist_prism < 0 || sp->n_dist_prism > 2 ||
+      (sp->n_dist_prism > 0 && (sp->dist_prism[0][5] < 3 || sp->dist_prism[0][5] > 32)) || (sp->n_dist_prism > 1 && (sp->dist_prism[1][5] < 3 || sp->dist_prism[1][5] > 32)) ||
       (sp->n_dist_tri > 0 && !sp->dist_tri) || !sp->cloud || !sp->csg) {
     set_error("pg_env_create: spec out of supported bounds"); return PG_ERR_INVALID;
   }
@@ -163,6 +164,15 @@ extern "C" int pg_env_create(const PgEnvSpec* sp, int device, PgEnv** out) {
   c.dist_tri = sp->n_dist_tri > 0 ? reinterpret_cast<const double*>(d + o_tri) : nullptr;
   c.tri_sphere = sp->n_dist_tri > 0 ? reinterpret_cast<const double*>(d + o_sph) : nullptr;
   c.tri_group_sphere = n_grp > 0 ? reinterpret_cast<const double*>(d + o_gsph) : nullptr;
+  c.n_dist_prism = sp->n_dist_prism;
+  for (int i = 0; i < sp->n_dist_prism; i++) {
+    const double* pr = sp->dist_prism[i];
+    const int n = (int)pr[5];
+    c.prism_sides[i] = n; c.prism_hh[i] = pr[4];
+    for (int k = 0; k < 3; k++) c.prism_c[i][k] = pr[k];
+    const double step = 2.0 * 3.14159265358979323846 / n;
+    for (int j = 0; j <= n; j++) { c.prism_v[i][j][0] = cos(step * (j % n)) * pr[3]; c.prism_v[i][j][1] = sin(step * (j % n)) * pr[3]; }
+  }
   c.clearance_h = sp->clearance_h; c.project_uses_clearance = sp->project_uses_clearance;
   c.clear_n = sp->n_clear_walls;
   for (int w = 0; w < sp->n_clear_walls && w < 2; w++) {

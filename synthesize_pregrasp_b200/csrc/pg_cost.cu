@@ -118,6 +118,7 @@ pcn_kernel(CostDev cd, const double* __restrict__ pose, const double* __restrict
         if (cd.n_dist_tri > 0) {
           d = tri_field(cd, qx, qy, qz, d);
         }
+        if (cd.n_dist_prism > 0) d = prism_field(cd, qx, qy, qz, d);
         s.df[p] = d;
         s.msk[p] = keep ? 0.f : -INFINITY;
       }

@@ -67,4 +67,30 @@ __device__ __forceinline__ float tri_field(const CostDev& cd, double qx, double 
   return fminf(d, (float)sqrt(best));
 }
 
+// exact unsigned distance to the SURFACE of the right prisms (the tessellated cylinders of distancefield_utils.py:62-68 in
+// closed form: caps and side strips of the tessellation are planar, so the triangle list and the prism are one surface).
+// 2D distance to the polygon boundary (min over its edges), inside test by the edge cross products, then the axial part.
+__device__ __forceinline__ float prism_field(const CostDev& cd, double qx, double qy, double qz, float d) {
+  for (int i = 0; i < cd.n_dist_prism; i++) {
+    const double x = qx - cd.prism_c[i][0], y = qy - cd.prism_c[i][1], z = qz - cd.prism_c[i][2];
+    double best = INFINITY;
+    bool inside = true;
+    const int n = cd.prism_sides[i];
+    for (int j = 0; j < n; j++) {
+      const double ax = cd.prism_v[i][j][0], ay = cd.prism_v[i][j][1];
+      const double ex = cd.prism_v[i][j + 1][0] - ax, ey = cd.prism_v[i][j + 1][1] - ay, wx = x - ax, wy = y - ay;
+      const double t = fmin(1.0, fmax(0.0, (wx * ex + wy * ey) / (ex * ex + ey * ey)));
+      const double dx = wx - t * ex, dy = wy - t * ey;
+      best = fmin(best, dx * dx + dy * dy);
+      inside = inside && (ex * wy - ey * wx >= 0);
+    }
+    const double dz = fabs(z) - cd.prism_hh[i];
+    double dist;
+    if (inside) dist = dz <= 0 ? fmin(sqrt(best), -dz) : dz;
+    else dist = dz <= 0 ? sqrt(best) : sqrt(best + dz * dz);
+    d = fminf(d, (float)dist);
+  }
+  return d;
+}
+
 }  // namespace pg

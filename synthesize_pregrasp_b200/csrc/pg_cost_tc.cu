@@ -23,10 +23,28 @@
 
 namespace pg {
 
-#define TC_THREADS 256
 #define TC_M 128
 #define TC_KC 32                         // conv4 K-chunk: channels of z staged per back-to-back step
 #define TC_N4 32                         // conv4 outputs padded to a legal MMA N
+#ifndef TC_NG
+#define TC_NG 4                          // column groups: threads per point row of a tile (the epilogues are latency bound: more warps)
+#endif
+#define TC_THREADS (TC_M * TC_NG)        // producer / epilogue threads
+#define TC_W1 (C1 / TC_NG)               // conv1 channels staged per thread
+#define TC_W2 (C2 / TC_NG)               // conv2 channels reduced per thread (pass 1)
+#define TC_WC (TC_KC / TC_NG)            // z channels per thread and K-chunk
+#define TC_W4 (TC_N4 / TC_NG)            // conv4 outputs per thread
+#ifdef TC_ABLATE_PASS1
+#define TC_P1_TILES(T) 0
+#else
+#define TC_P1_TILES(T) (T)
+#endif
+#ifdef TC_ABLATE_CHUNKS
+#define TC_NCHUNK 0
+#else
+#define TC_NCHUNK (C3 / TC_KC)
+#endif
+#define TC_NT (TC_THREADS + 32)           // + one warp whose lane 0 issues every tcgen05.mma
 
 struct TcSmem {
   float w32_hi[C1 * C3], w32_lo[C1 * C3];   // (W3a W2)  [256 x 32]  canonical K-major: [(k/4)][n][k%4]
@@ -42,18 +60,16 @@ struct TcSmem {
   float lat[LAT + 2];
   double pose[7], R[9], fin[6];
   unsigned char msk[P_CLOUD];
-  unsigned long long mbar, mbar_w, mbar_b[2];
+  unsigned long long mbar_w, full[2], done[2];   // weights landed | operand buffer b written by the 8 producer warps | MMAs reading buffer b complete
   unsigned int tmem_base;
   int count;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// round-to-nearest (ties away) to tf32 = what cvt.rna.tf32.f32 returns for finite inputs, in two integer operations
+// (the compiler expands the cvt with an inf / nan path that the epilogues issue 16 times per thread and K-chunk)
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 // no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -105,6 +121,21 @@ __device__ __forceinline__ void mma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(mbar) : "memory");
+}
+// a producer warp publishes its part of an operand buffer: generic-proxy stores -> async proxy, order the warp's TMEM reads,
+// then one arrival per warp (the barriers count the producer warps)
+__device__ __forceinline__ void publish(uint32_t mbar, int lane) {
+#if !defined(TC_ABLATE_FENCE)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncwarp();
+  if (lane == 0) mbar_arrive(mbar);
+}
+#define TC_PRODUCER_SYNC() asm volatile("bar.sync 1, %0;" :: "n"(TC_THREADS) : "memory")     // the producer warps only
+
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   uint32_t done;
   do {
@@ -124,6 +155,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),     \
                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                        \
                : "r"(taddr))
+#define TC_LD8(v, taddr)                                                                                                        \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                                  \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr))
+template <int W> __device__ __forceinline__ void tc_ld(uint32_t* v, uint32_t taddr) {
+  if (W == 16) { TC_LD16(v, taddr); } else { TC_LD8(v, taddr); }
+}
 #define TC_LD_WAIT() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 
 __device__ __forceinline__ float tc_box_dist(double x, double y, double z, const double* lo, const double* hi) {
@@ -134,12 +171,12 @@ __device__ __forceinline__ float tc_box_dist(double x, double y, double z, const
   return (float)(outside > 0 ? outside : fmax(inside, 0.0));
 }
 
-// conv1 + ReLU for 16 of the 32 channels of point p (thread (row, grp): channels 16 grp ..), split into tf32 hi / lo and
+// conv1 + ReLU for TC_W1 of the 32 channels of point p (thread (row, grp): channels TC_W1 grp ..), split into tf32 hi / lo and
 // stored as the A operand of the next GEMM; rows beyond the cloud are zero
 __device__ __forceinline__ void stage_h1(TcSmem& s, const CostDev& cd, int p, int P, int row, int grp, float* dst_hi, float* dst_lo) {
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const int j = 16 * grp + 4 * q;
+  for (int q = 0; q < TC_W1 / 4; q++) {
+    const int j = TC_W1 * grp + 4 * q;
     float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
     if (p < P) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(cd.a1 + (size_t)p * C1 + j));
@@ -155,14 +192,16 @@ __device__ __forceinline__ void stage_h1(TcSmem& s, const CostDev& cd, int p, in
   }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_NT, 1)
 pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const double* __restrict__ fins, int B, float* __restrict__ latent) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid & (TC_M - 1), grp = tid >> 7;        // TMEM lane / point row of this thread, column half
+  const int row = tid & (TC_M - 1), grp = (tid >> 7) & (TC_NG - 1);  // producers: TMEM lane / point row of this thread, column group
+  const bool issuer = warp == TC_THREADS / 32;             // the extra warp: lane 0 issues the MMAs, never touches operands or TMEM data
   const int P = cd.n_cloud;
-  const uint32_t mbar = smem_u32(&s.mbar), mbar_w = smem_u32(&s.mbar_w);
+  const uint32_t mbar_w = smem_u32(&s.mbar_w);
+  const uint32_t full0 = smem_u32(&s.full[0]), full1 = smem_u32(&s.full[1]), done0 = smem_u32(&s.done[0]), done1 = smem_u32(&s.done[1]);
 
   // ---- one-time setup: TMEM allocation, mbarriers, weight operands by TMA bulk copies
   if (warp == 0) {
@@ -170,10 +209,11 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_w));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s.mbar_b[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s.mbar_b[1])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(full0), "n"(TC_THREADS / 32));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(full1), "n"(TC_THREADS / 32));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(done0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(done1));
     asm volatile("fence.mbarrier_init.release.cluster;");
     const uint32_t bytes = 4u * (2 * C1 * C3 + 2 * C3 * TC_N4 + 2 * C1 * C2);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_w), "r"(bytes) : "memory");
@@ -189,13 +229,16 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
   asm volatile("tcgen05.fence::after_thread_sync;");
   mbar_wait(mbar_w, 0);                                    // weights landed (async proxy writes, visible to the tensor core)
   const uint32_t tmem = s.tmem_base;
-  const uint32_t tm_d3 = tmem, tm_d4 = tmem + C3, tm_d2 = tmem;          // D3: columns 0..255, D4: 256..287, D2 (pass 1) aliases D3
+  const uint32_t tm_d3 = tmem, tm_d4 = tmem + C3, tm_d2 = tmem;          // D3: columns 0..255, D4: 256..287, D2[0|1] (pass 1) alias D3
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const OpDesc d_a1 = make_opdesc<TC_M>(smem_u32(s.a1_hi), smem_u32(s.a1_lo)), d_a4 = make_opdesc<TC_M>(smem_u32(s.a4_hi), smem_u32(s.a4_lo));
   const OpDesc d_w32 = make_opdesc<C3>(smem_u32(s.w32_hi), smem_u32(s.w32_lo)), d_w2 = make_opdesc<C2>(smem_u32(s.w2_hi), smem_u32(s.w2_lo));
   const OpDesc d_w4 = make_opdesc<TC_N4>(smem_u32(s.w4_hi), smem_u32(s.w4_lo));
-  const uint32_t mbar_b0 = smem_u32(&s.mbar_b[0]), mbar_b1 = smem_u32(&s.mbar_b[1]);
-  uint32_t phase = 0, ph0 = 0, ph1 = 0;     // parities of mbar (D3 GEMM) and of the two operand-buffer barriers
+  // Producer / consumer protocol.  Operand buffer 0 = a4, buffer 1 = a1.  full[b]: the 8 producer warps have written buffer b
+  // (one arrival per warp); done[b]: the MMAs that read buffer b have completed (tcgen05.commit by the issuer).  Each side keeps
+  // the parities of the barriers it waits on; both walk the same sequence of tiles / K-chunks.
+  uint32_t pf0 = 0, pf1 = 0, pd0 = 0, pd1 = 0;
+  const int T = (P + TC_M - 1) / TC_M;
 
   for (int e = blockIdx.x; e < B; e += gridDim.x) {
     // ---------------- stage 0: geometry (identical to pcn_kernel<true>)
@@ -211,7 +254,12 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
     }
     __syncthreads();
     int cnt = 0;
-    for (int p = tid; p < P; p += TC_THREADS) {
+#if defined(TC_ABLATE_GEOM)
+    for (int p = tid; p < P; p += TC_NT) { s.df[p] = 0.01f; s.msk[p] = 1; cnt++; }
+    for (int p = tid; p < 0; p += TC_NT) {
+#else
+    for (int p = tid; p < P; p += TC_NT) {
+#endif
       double cx = cd.cloud[3 * p], cy = cd.cloud[3 * p + 1], cz = cd.cloud[3 * p + 2];
       double wx = s.R[0] * cx + s.R[1] * cy + s.R[2] * cz + s.pose[0];
       double wy = s.R[3] * cx + s.R[4] * cy + s.R[5] * cz + s.pose[1];
@@ -226,6 +274,7 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
       float d = INFINITY;
       for (int b = 0; b < cd.n_dist_box; b++) d = fminf(d, tc_box_dist(qx, qy, qz, cd.dist_box[b][0], cd.dist_box[b][1]));
       if (cd.n_dist_tri > 0) d = tri_field(cd, qx, qy, qz, d);
+      if (cd.n_dist_prism > 0) d = prism_field(cd, qx, qy, qz, d);
       s.df[p] = d;
       s.msk[p] = keep ? 1 : 0;
       cnt += keep;
@@ -234,7 +283,7 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
       double fx = s.fin[3 * f], fy = s.fin[3 * f + 1], fz = s.fin[3 * f + 2];
       double best = INFINITY;
       int bi = 0x7fffffff;
-      for (int p = tid; p < P; p += TC_THREADS) {
+      for (int p = tid; p < P; p += TC_NT) {
         double dx = cd.cloud[3 * p] - fx, dy = cd.cloud[3 * p + 1] - fy, dz = cd.cloud[3 * p + 2] - fz;
         double dd = dx * dx + dy * dy + dz * dz;
         if (dd < best) { best = dd; bi = p; }
@@ -245,12 +294,12 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
         if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
       }
       double* rb = reinterpret_cast<double*>(s.red);
-      int* ri = reinterpret_cast<int*>(s.red + 32);
+      int* ri = reinterpret_cast<int*>(s.red + 64);             // behind the (up to 17) doubles of rb
       __syncthreads();
       if (lane == 0) { rb[warp] = best; ri[warp] = bi; }
       __syncthreads();
       if (tid == 0) {
-        for (int w = 1; w < TC_THREADS / 32; w++) if (rb[w] < best || (rb[w] == best && ri[w] < bi)) { best = rb[w]; bi = ri[w]; }
+        for (int w = 1; w < TC_NT / 32; w++) if (rb[w] < best || (rb[w] == best && ri[w] < bi)) { best = rb[w]; bi = ri[w]; }
         bool ok = fz > cd.clearance_h;
         if (cd.project_uses_clearance) {
           ok = !(fz < cd.clearance_h);
@@ -273,7 +322,7 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
     __syncthreads();
     if (tid == 0) {
       int t = 0;
-      for (int w = 0; w < TC_THREADS / 32; w++) t += reinterpret_cast<int*>(s.red)[w];
+      for (int w = 0; w < TC_NT / 32; w++) t += reinterpret_cast<int*>(s.red)[w];
       s.count = t;
     }
     __syncthreads();
@@ -283,172 +332,186 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
       continue;
     }
 
-    // ---------------- pass 1: g = masked max over points of conv2 (tcgen05, N = 64); thread (row, grp): channels 32 grp ..
-    float gmax[32];
-#pragma unroll
-    for (int c = 0; c < 32; c++) gmax[c] = -INFINITY;
-    // software pipeline over the tiles: two operand buffers (a1, a4) and two accumulator regions (D2[0], D2[1]); the tensor
-    // core works on tile t + 1 while the CUDA cores reduce tile t
-    {
-      const int T = (P + TC_M - 1) / TC_M;
-      stage_h1(s, cd, row, P, row, grp, s.a1_hi, s.a1_lo);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-      asm volatile("tcgen05.fence::before_thread_sync;");
-      __syncthreads();
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        gemm_split3<C2, C1>(tm_d2, d_a1, d_w2, 0u);
-        mma_commit(mbar_b0);
-      }
-      for (int t = 0; t < T; t++) {
-        const int b = t & 1;
-        if (t + 1 < T) {                                             // stage and launch tile t + 1 into the other buffer / region
-          stage_h1(s, cd, (t + 1) * TC_M + row, P, row, grp, b ? s.a1_hi : s.a4_hi, b ? s.a1_lo : s.a4_lo);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;");
-          __syncthreads();                                           // (also: everyone has read D2[1 - b] of tile t - 1)
-          if (tid == 0) {
+    if (issuer) {
+      // ================= MMA issuer (one thread): waits for operand buffers, feeds the tensor core, signals completion
+      if (lane == 0) {
+        for (int t = 0; t < TC_P1_TILES(T); t++) {                                  // pass 1: D2[t & 1] = h1 tile . W2^T
+          const int b = t & 1;
+          if (b) { mbar_wait(full1, pf1); pf1 ^= 1; } else { mbar_wait(full0, pf0); pf0 ^= 1; }
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          gemm_split3<C2, C1>(tm_d2 + (uint32_t)(b * C2), b ? d_a1 : d_a4, d_w2, 0u);
+          mma_commit(b ? done1 : done0);
+        }
+        for (int t = 0; t < T; t++) {                                  // pass 2
+          mbar_wait(full1, pf1); pf1 ^= 1;
+          asm volatile("tcgen05.fence::after_thread_sync;");
+#if !defined(TC_ABLATE_MMA3)
+          gemm_split3<C3, C1>(tm_d3, d_a1, d_w32, 0u);                 // D3 = h1 tile . (W3a W2)^T
+#endif
+          mma_commit(done1);
+#pragma unroll 1
+          for (int ch = 0; ch < TC_NCHUNK; ch++) {                    // D4 += z chunk . W4 chunk^T
+            const int b = ch & 1;
+            if (b) { mbar_wait(full1, pf1); pf1 ^= 1; } else { mbar_wait(full0, pf0); pf0 ^= 1; }
             asm volatile("tcgen05.fence::after_thread_sync;");
-            gemm_split3<C2, C1>(tm_d2 + (b ? 0u : (uint32_t)C2), b ? d_a1 : d_a4, d_w2, 0u);
-            mma_commit(b ? mbar_b0 : mbar_b1);
+            // W4 chunk: K rows 32 ch .. of the [32 x 256] operand = byte offset (32 ch / 4) * (N * 16), in descriptor units (>> 4)
+            const uint64_t boff = (uint64_t)((TC_KC * ch / 4) * (TC_N4 * 16) >> 4);
+            OpDesc w4c; w4c.hi = d_w4.hi + boff; w4c.lo = d_w4.lo + boff;
+#if !defined(TC_ABLATE_MMA4)
+            gemm_split3<TC_N4, TC_KC>(tm_d4, b ? d_a1 : d_a4, w4c, ch > 0 ? 1u : 0u);
+#endif
+            mma_commit(b ? done1 : done0);
           }
         }
-        if (b) { mbar_wait(mbar_b1, ph1); ph1 ^= 1; } else { mbar_wait(mbar_b0, ph0); ph0 ^= 1; }
+      }
+      __syncwarp();
+    } else {
+      // ================= producers / epilogue (TC_NG warps per TMEM lane quadrant; thread (row, grp))
+      // ---------------- pass 1: g = masked max over points of conv2 (N = 64); this thread: channels TC_W2 grp .. of its row.
+      // Software pipeline over the tiles: tile t + 1 is staged (other buffer, other accumulator region) before tile t is reduced.
+      float gmax[TC_W2];
+#pragma unroll
+      for (int c = 0; c < TC_W2; c++) gmax[c] = -INFINITY;
+#if !defined(TC_ABLATE_PASS1)
+      stage_h1(s, cd, row, P, row, grp, s.a4_hi, s.a4_lo);
+      publish(full0, lane);
+#endif
+      for (int t = 0; t < TC_P1_TILES(T); t++) {
+        const int b = t & 1;
+        if (t + 1 < T) {                 // buffer 1 - b / D2[1 - b] were released when this thread finished tile t - 1
+          stage_h1(s, cd, (t + 1) * TC_M + row, P, row, grp, b ? s.a4_hi : s.a1_hi, b ? s.a4_lo : s.a1_lo);
+          publish(b ? full0 : full1, lane);
+        }
+        if (b) { mbar_wait(done1, pd1); pd1 ^= 1; } else { mbar_wait(done0, pd0); pd0 ^= 1; }
         asm volatile("tcgen05.fence::after_thread_sync;");
         const int p = t * TC_M + row;
         const bool keep = p < P && s.msk[p];
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
+        for (int part = 0; part < TC_W2 / 16; part++) {
           uint32_t v[16];
-          TC_LD16(v, tm_d2 + (uint32_t)(b * C2) + lane_base + (uint32_t)(32 * grp + 16 * half));
+          TC_LD16(v, tm_d2 + (uint32_t)(b * C2) + lane_base + (uint32_t)(TC_W2 * grp + 16 * part));
           TC_LD_WAIT();
           if (keep) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) gmax[16 * half + i] = fmaxf(gmax[16 * half + i], __uint_as_float(v[i]) + s.b2[32 * grp + 16 * half + i]);
+            for (int i = 0; i < 16; i++) gmax[16 * part + i] = fmaxf(gmax[16 * part + i], __uint_as_float(v[i]) + s.b2[TC_W2 * grp + 16 * part + i]);
           }
         }
       }
-    }
 #pragma unroll
-    for (int c = 0; c < 32; c++) {
-      float v = gmax[c];
-      for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-      gmax[c] = v;
-    }
-    if (lane == 0) {
+      for (int c = 0; c < TC_W2; c++) {
+        float v = gmax[c];
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        gmax[c] = v;
+      }
+      if (lane == 0) {
 #pragma unroll
-      for (int c = 0; c < 32; c++) s.red[warp * 32 + c] = gmax[c];   // the four warps of half `grp` hold channels 32 grp ..
-    }
-    __syncthreads();
-    if (tid < C2) {
-      const int h = tid / 32, c = tid % 32;
-      float v = s.red[(4 * h) * 32 + c];
-      for (int w = 1; w < 4; w++) v = fmaxf(v, s.red[(4 * h + w) * 32 + c]);
-      s.g[tid] = v;
-    }
-    __syncthreads();
-    if (tid < C3) {                                                  // c = (b3 + W3a b2) + W3b g
-      float wk[C2];                                                  // all 64 loads in flight at once (they were a dependent L2-latency chain)
+        for (int c = 0; c < TC_W2; c++) s.red[warp * TC_W2 + c] = gmax[c];   // the four warps of group `grp` hold channels TC_W2 grp ..
+      }
+      TC_PRODUCER_SYNC();
+      if (tid < C2) {
+        const int h = tid / TC_W2, c = tid % TC_W2;
+        float v = s.red[(4 * h) * TC_W2 + c];
+        for (int w = 1; w < 4; w++) v = fmaxf(v, s.red[(4 * h + w) * TC_W2 + c]);
+        s.g[tid] = v;
+      }
+      TC_PRODUCER_SYNC();
+      if (tid < C3) {                                                  // c = (b3 + W3a b2) + W3b g
+        float v = tw.cbase[tid];
 #pragma unroll
-      for (int k = 0; k < C2; k++) wk[k] = __ldg(cd.w3bt + k * C3 + tid);
-      float v = tw.cbase[tid];
+        for (int k0 = 0; k0 < C2; k0 += 32) {                          // 32 loads in flight at a time (they were a dependent L2-latency chain)
+          float wk[32];
 #pragma unroll
-      for (int k = 0; k < C2; k++) v = fmaf(wk[k], s.g[k], v);
-      s.c[tid] = v;
-    }
-    __syncthreads();
+          for (int k = 0; k < 32; k++) wk[k] = __ldg(cd.w3bt + (k0 + k) * C3 + tid);
+#pragma unroll
+          for (int k = 0; k < 32; k++) v = fmaf(wk[k], s.g[k0 + k], v);
+        }
+        s.c[tid] = v;
+      }
+      TC_PRODUCER_SYNC();
 
-    // ---------------- pass 2: per 128-point tile  h1 -> [tcgen05 D3] -> z chunks -> [tcgen05 D4] -> masked max
-    float rmax[16];                                                  // thread (row, grp): conv4 outputs 16 grp .. (outputs >= 20 are padding)
+      // ---------------- pass 2: per 128-point tile  h1 -> [D3] -> z chunks -> [D4] -> masked max
+      float rmax[TC_W4];                                               // conv4 outputs TC_W4 grp .. of this row (outputs >= 20 are padding)
 #pragma unroll
-    for (int o = 0; o < 16; o++) rmax[o] = -INFINITY;
-    for (int t0 = 0; t0 < P; t0 += TC_M) {
-      const int p = t0 + row;
-      stage_h1(s, cd, p, P, row, grp, s.a1_hi, s.a1_lo);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;");
-      __syncthreads();                                               // (also: D3 / D4 of the previous tile have been read by everyone)
-      if (tid == 0) {
+      for (int o = 0; o < TC_W4; o++) rmax[o] = -INFINITY;
+      for (int t = 0; t < T; t++) {
+        const int p = t * TC_M + row;
+        stage_h1(s, cd, p, P, row, grp, s.a1_hi, s.a1_lo);           // a1 is free: its last reader (chunk 7 of the previous tile) was waited for
+        publish(full1, lane);
+        mbar_wait(done1, pd1); pd1 ^= 1;                               // D3 complete
         asm volatile("tcgen05.fence::after_thread_sync;");
-        gemm_split3<C3, C1>(tm_d3, d_a1, d_w32, 0u);
-        mma_commit(mbar);
-      }
-      mbar_wait(mbar, phase); phase ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      // back-to-back: z chunk ch (channels 32 ch ..) = relu(D3 + c) -> shared memory (tf32 hi / lo) -> D4 += z_chunk . W4_chunk^T.
-      // Two operand buffers (a4, and a1 -- free once D3 is complete): the tensor core works on chunk ch while the CUDA cores
-      // prepare chunk ch + 1; a buffer is rewritten only after the MMAs of two chunks earlier have completed.
+        // back-to-back: z chunk ch (channels 32 ch ..) = relu(D3 + c) -> shared memory (tf32 hi / lo) -> D4 += z_chunk . W4_chunk^T.
+        // Two operand buffers (a4, and a1 -- free once D3 is complete): a buffer is rewritten only after the MMAs of two chunks
+        // earlier have completed; nobody waits for anybody else otherwise.
 #pragma unroll 1
-      for (int ch = 0; ch < C3 / TC_KC; ch++) {
-        const int b = ch & 1;
-        uint32_t v[16];
-        TC_LD16(v, tm_d3 + lane_base + (uint32_t)(TC_KC * ch + 16 * grp));
-        TC_LD_WAIT();
-        float4 hi[4], lo[4];
+        for (int ch = 0; ch < TC_NCHUNK; ch++) {
+          const int b = ch & 1;
+          uint32_t v[TC_WC];
+#if defined(TC_ABLATE_EPI3)
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const float4 cc = *reinterpret_cast<const float4*>(s.c + TC_KC * ch + 16 * grp + 4 * q);
-          const float z0 = fmaxf(__uint_as_float(v[4 * q]) + cc.x, 0.f), z1 = fmaxf(__uint_as_float(v[4 * q + 1]) + cc.y, 0.f);
-          const float z2 = fmaxf(__uint_as_float(v[4 * q + 2]) + cc.z, 0.f), z3 = fmaxf(__uint_as_float(v[4 * q + 3]) + cc.w, 0.f);
-          hi[q] = make_float4(tf32_rna(z0), tf32_rna(z1), tf32_rna(z2), tf32_rna(z3));
-          lo[q] = make_float4(z0 - hi[q].x, z1 - hi[q].y, z2 - hi[q].z, z3 - hi[q].w);
-        }
-        if (ch >= 2) { if (b) { mbar_wait(mbar_b1, ph1); ph1 ^= 1; } else { mbar_wait(mbar_b0, ph0); ph0 ^= 1; } }
-        float* dh = b ? s.a1_hi : s.a4_hi;
-        float* dl = b ? s.a1_lo : s.a4_lo;
+          for (int i = 0; i < TC_WC; i++) v[i] = 0;
+#else
+          tc_ld<TC_WC>(v, tm_d3 + lane_base + (uint32_t)(TC_KC * ch + TC_WC * grp));
+          TC_LD_WAIT();
+#endif
+          float4 hi[TC_WC / 4], lo[TC_WC / 4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int o = ((4 * grp + q) * TC_M + row) * 4;
-          *reinterpret_cast<float4*>(dh + o) = hi[q];
-          *reinterpret_cast<float4*>(dl + o) = lo[q];
+          for (int q = 0; q < TC_WC / 4; q++) {
+            const float4 cc = *reinterpret_cast<const float4*>(s.c + TC_KC * ch + TC_WC * grp + 4 * q);
+            const float z0 = fmaxf(__uint_as_float(v[4 * q]) + cc.x, 0.f), z1 = fmaxf(__uint_as_float(v[4 * q + 1]) + cc.y, 0.f);
+            const float z2 = fmaxf(__uint_as_float(v[4 * q + 2]) + cc.z, 0.f), z3 = fmaxf(__uint_as_float(v[4 * q + 3]) + cc.w, 0.f);
+            hi[q] = make_float4(tf32_rna(z0), tf32_rna(z1), tf32_rna(z2), tf32_rna(z3));
+            lo[q] = make_float4(z0 - hi[q].x, z1 - hi[q].y, z2 - hi[q].z, z3 - hi[q].w);
+          }
+          if (ch >= 2) { if (b) { mbar_wait(done1, pd1); pd1 ^= 1; } else { mbar_wait(done0, pd0); pd0 ^= 1; } }
+          float* dh = b ? s.a1_hi : s.a4_hi;
+          float* dl = b ? s.a1_lo : s.a4_lo;
+#if !defined(TC_ABLATE_EPI3)
+#pragma unroll
+          for (int q = 0; q < TC_WC / 4; q++) {
+            const int o = (((TC_WC / 4) * grp + q) * TC_M + row) * 4;
+            *reinterpret_cast<float4*>(dh + o) = hi[q];
+            *reinterpret_cast<float4*>(dl + o) = lo[q];
+          }
+#endif
+          publish(b ? full1 : full0, lane);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();
-        if (tid == 0) {
-          asm volatile("tcgen05.fence::after_thread_sync;");
-          // W4 chunk: K rows 32 ch .. of the [32 x 256] operand = byte offset (32 ch / 4) * (N * 16), in descriptor units (>> 4)
-          const uint64_t boff = (uint64_t)((TC_KC * ch / 4) * (TC_N4 * 16) >> 4);
-          OpDesc w4c; w4c.hi = d_w4.hi + boff; w4c.lo = d_w4.lo + boff;
-          gemm_split3<TC_N4, TC_KC>(tm_d4, b ? d_a1 : d_a4, w4c, ch > 0 ? 1u : 0u);
-          mma_commit(b ? mbar_b1 : mbar_b0);
+#if !defined(TC_ABLATE_CHUNKS)
+        mbar_wait(done0, pd0); pd0 ^= 1;                               // the last two chunks' MMAs
+        mbar_wait(done1, pd1); pd1 ^= 1;
+#endif
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        {
+          uint32_t v[TC_W4];
+          tc_ld<TC_W4>(v, tm_d4 + lane_base + (uint32_t)(TC_W4 * grp));
+          TC_LD_WAIT();
+          const float m = (p < P && s.msk[p]) ? 0.f : -INFINITY;
+#pragma unroll
+          for (int o = 0; o < TC_W4; o++) rmax[o] = fmaxf(rmax[o], __uint_as_float(v[o]) + s.b4[TC_W4 * grp + o] + m);
         }
       }
-      mbar_wait(mbar_b0, ph0); ph0 ^= 1;                             // the last two chunks' MMAs
-      mbar_wait(mbar_b1, ph1); ph1 ^= 1;
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      {
-        uint32_t v[16];
-        TC_LD16(v, tm_d4 + lane_base + (uint32_t)(16 * grp));
-        TC_LD_WAIT();
-        const float m = (p < P && s.msk[p]) ? 0.f : -INFINITY;
+      // reduce rmax over the 128 rows
 #pragma unroll
-        for (int o = 0; o < 16; o++) rmax[o] = fmaxf(rmax[o], __uint_as_float(v[o]) + s.b4[16 * grp + o] + m);
+      for (int o = 0; o < TC_W4; o++) {
+        float v = rmax[o];
+        for (int k = 16; k > 0; k >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, k));
+        rmax[o] = v;
       }
-    }
-    // reduce rmax over the 128 rows
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      if (lane == 0) {
 #pragma unroll
-    for (int o = 0; o < 16; o++) {
-      float v = rmax[o];
-      for (int k = 16; k > 0; k >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, k));
-      rmax[o] = v;
+        for (int o = 0; o < TC_W4; o++) s.red[warp * TC_W4 + o] = rmax[o];
+      }
+      TC_PRODUCER_SYNC();
+      if (tid < C4) {
+        const int h = tid / TC_W4, o = tid % TC_W4;
+        float v = s.red[(4 * h) * TC_W4 + o];
+        for (int w = 1; w < 4; w++) v = fmaxf(v, s.red[(4 * h + w) * TC_W4 + o]);
+        s.lat[tid] = v;
+      }
+      TC_PRODUCER_SYNC();
+      if (tid < LAT) latent[(size_t)e * LAT + tid] = s.lat[tid];
     }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-      for (int o = 0; o < 16; o++) s.red[warp * 16 + o] = rmax[o];
-    }
-    __syncthreads();
-    if (tid < C4) {
-      const int h = tid / 16, o = tid % 16;
-      float v = s.red[(4 * h) * 16 + o];
-      for (int w = 1; w < 4; w++) v = fmaxf(v, s.red[(4 * h + w) * 16 + o]);
-      s.lat[tid] = v;
-    }
-    __syncthreads();
-    if (tid < LAT) latent[(size_t)e * LAT + tid] = s.lat[tid];
-    __syncthreads();
+    __syncthreads();                                                   // producers and issuer meet; shared scratch is free for the next evaluation
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
@@ -463,7 +526,7 @@ int launch_cost_tc(PgEnv* env, const double* pose, const double* fins, int B, fl
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->device);
   int grid = sms < B ? sms : B;
-  pcn_tc_kernel<<<grid, TC_THREADS, smem, st>>>(env->cost, env->tcw, pose, fins, B, latent);
+  pcn_tc_kernel<<<grid, TC_NT, smem, st>>>(env->cost, env->tcw, pose, fins, B, latent);
   count_launch();
   PG_CUDA(cudaGetLastError());
   return PG_OK;

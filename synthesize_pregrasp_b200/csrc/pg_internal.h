@@ -30,6 +30,10 @@ struct CostDev {                 // device pointers of the cost stage constants
   const double* dist_tri;
   const double* tri_sphere;      // [n_dist_tri][4]: centroid and radius of each triangle's bounding sphere
   const double* tri_group_sphere; // [ceil(n_dist_tri/16)][4]: bounding sphere of each group of 16 consecutive triangles
+  int n_dist_prism;               // right prisms (regular polygon cross-section, axis z): tessellated cylinders in closed form
+  int prism_sides[2];
+  double prism_c[2][3], prism_hh[2];
+  double prism_v[2][33][2];       // polygon vertices (closed: v[sides] = v[0]), counter-clockwise
   double clearance_h;
   int project_uses_clearance;     // 1: checkClearance(local point) incl. the walls (bookshelf_graph_env.py:683-689)
   int clear_n;

@@ -95,6 +95,7 @@ class EnvSpec:
     dummy_states: Optional[np.ndarray] = None     # non-validate CSG (model_test.py:86-87)
     csg_states: Optional[np.ndarray] = None       # --validate CSG
     paths_id: Optional[np.ndarray] = None
+    dist_prisms: Optional[np.ndarray] = None      # [n,6] (cx, cy, cz, r, half height, sides): dist_tris' polyhedra in closed form
 
     @property
     def substeps_per_rollout(self) -> int:
@@ -337,6 +338,9 @@ def make_spec(env: str) -> EnvSpec:
             deocclude_boxes=_box_aabbs([((-0.04, -0.045, 0.005), (0.05, 0.045, _BIG)),
                                         ((0.05, -_BIG, 0.005), (_BIG, _BIG, _BIG))]),        # :633-636
             dist_boxes=_box_aabbs([floor_dist, _o3d_box(0.1, 0.4, 0.4, (-0.15, -0.2, 0))]), dist_tris=tris,
+            # the two tessellated holders in closed form (20-sided prisms, Open3D's default resolution): what the kernels evaluate;
+            # the triangle list above is what the oracle evaluates
+            dist_prisms=np.array([[0, -0.1, 0.11, 0.045, 0.11, 20], [0, 0.1, 0.11, 0.045, 0.11, 20]], np.float64),
             region_type=REGION_WATERBOTTLE, settle_substeps=300, metric_axis=0, metric_offset=0.0,   # :507-560
             cloud=pts, cloud_normals=nrm, dummy_states=dummy, csg_states=csg, paths_id=paths)
     raise KeyError(f"unknown env {env!r}")

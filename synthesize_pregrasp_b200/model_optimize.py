@@ -50,6 +50,7 @@ def build_parser():
     p.add_argument("--batched", action="store_true", help="all paths x runs as one multi-problem launch per iteration")
     p.add_argument("--max_paths", type=int, default=10, help="paths taken from paths_id.npy (the reference file holds 10)")
     p.add_argument("--out_dir", type=str, default="data")
+    p.add_argument("--no_record", action="store_true", help="skip the model_test.py replay / recording that follows every path (model_optimize.py:107-110)")
     return p
 
 
@@ -115,9 +116,25 @@ def run(args):
                     if _Jopt > best["best"]:
                         best.update(best=float(_Jopt), uopt=_uopt, Jopt_log=_Jopt_log, r_log=_r_log)
                 results.append(best)
-        for r in results:
-            # as the reference, every path overwrites the same three files; the last path's result stays (model_optimize.py:100-102)
+        for i, r in enumerate(results):
+            # The reference saves these three files after EACH path and then replays / records the result with model_test.py
+            # (model_optimize.py:97-110), so at any time they hold the path optimised last; under --validate it stops at the first
+            # path whose grasps pass validate_path (:112-117).  That screening (Drake IK) is not part of this
+            # package, so ALL paths are optimised here: the un-suffixed files end up holding the LAST path -- what the reference
+            # leaves behind when no path passes -- and every path additionally keeps its own copy (`..._path<i>`) together with
+            # its model_test recording, so that a later `model_test --validate --path_id i` replays controls against the path
+            # they were optimised for.
             _save(args.out_dir, args.exp_name, max_force, r["Jopt_log"], r["r_log"], r["uopt"])
+            if len(results) > 1 or args.validate:
+                _save(args.out_dir, f"{args.exp_name}_path{i}", max_force, r["Jopt_log"], r["r_log"], r["uopt"])
+            if not args.no_record:
+                from . import model_test as MT
+                tips, poses, _, _ = MT.record(args.env, r["uopt"], max_force, r["path"], args.validate)
+                for sub in ("tip_data", "object_poses"):
+                    os.makedirs(os.path.join(args.out_dir, sub), exist_ok=True)
+                for name in ([f"{args.exp_name}_{max_force}"] + ([f"{args.exp_name}_path{i}_{max_force}"] if len(results) > 1 or args.validate else [])):
+                    np.save(os.path.join(args.out_dir, "tip_data", f"{name}_tip_poses.npy"), tips)
+                    np.save(os.path.join(args.out_dir, "object_poses", f"{name}_object_poses.npy"), poses)
             line = f"Max force: {max_force} mean rewards: {r['mean']}, best rewards:{r['best']}\n"
             print(line, end="")
             f.writelines(line)

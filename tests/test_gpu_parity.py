@@ -388,6 +388,12 @@ def test_model_optimize_driver_serial_and_batched(EN, tmp_path):
                                                 "--runs", "1", "--max_paths", "2", "--batched", "--exp_name", "v",
                                                 "--out_dir", str(tmp_path / "validate")]))
     assert [r["path"] for r in resv] == [[1, 2], [1, 7]] and all(np.isfinite(r["best"]) for r in resv)
+    # every path keeps its own controls and model_test recording (the un-suffixed files hold the path optimised last, as the
+    # reference's would when no path passes its validate_path screening, model_optimize.py:97-117)
+    for i, r in enumerate(resv):
+        np.testing.assert_array_equal(np.load(tmp_path / "validate" / "traj" / f"v_path{i}_20.0.npy"), r["uopt"])
+        assert np.load(tmp_path / "validate" / "object_poses" / f"v_path{i}_20.0_object_poses.npy").shape == (100, 7)
+    np.testing.assert_array_equal(np.load(tmp_path / "validate" / "traj" / "v_20.0.npy"), resv[-1]["uopt"])
 
 
 def test_model_test_recording_mirror(EN, tmp_path):
