@@ -172,6 +172,12 @@ int pg_carry_destroy(PgCarry* carry);
 int pg_env_step_single(PgEnv* env, PgCarry* carry, const double* a_host, int32_t state, double max_force, int32_t last_step,
                        double* reward_host, double* metric_host, double* pose7_host, double* trace_host);
 
+/* diagnostics / tuning: how pg_rollout, pg_rollout_multi and pg_physics run the rigid-body part.  0 / 1 (default): one persistent
+ * launch for the whole episode; 2: one launch per episode phase with the rollouts re-sorted by solver work between phases (the
+ * measured alternative decomposition; slower on the B200).  Results are bit-identical either way (a rollout's
+ * arithmetic does not depend on the thread that runs it). */
+int pg_set_rollout_mode(PgEnv* env, int mode);
+
 /* diagnostics: number of kernel launches issued through this library since load */
 uint64_t pg_launch_count(void);
 

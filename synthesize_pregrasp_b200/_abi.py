@@ -184,6 +184,7 @@ def lib():
     L.pg_dyn_sweep_simple.argtypes = [vp, vp, i32, f64, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp]
     L.pg_dyn_feasible_qp.argtypes = [vp, vp, vp, i32, i32, f64, f64, f64, vp, vp, vp]
     L.pg_dyn_sweep_qp.argtypes = [vp, vp, i32, f64, f64, f64, f64, C.c_uint64, C.c_uint64, vp, C.c_uint64, vp, vp]
+    L.pg_set_rollout_mode.argtypes = [vp, i32]
     L.pg_carry_create.argtypes = [vp, C.POINTER(vp)]
     L.pg_carry_reset.argtypes = [vp, _DP]
     L.pg_carry_destroy.argtypes = [vp]
@@ -198,7 +199,7 @@ def lib():
 
 EXPORTS = ("pg_last_error", "pg_version", "pg_env_create", "pg_env_destroy", "pg_rollout", "pg_rollout_multi", "pg_rollout_host", "pg_physics",
            "pg_cost", "pg_score", "pg_mppi_update", "pg_mppi_merge_apply", "pg_dyn_feasible_simple", "pg_dyn_sweep_simple",
-           "pg_dyn_feasible_qp", "pg_dyn_sweep_qp", "pg_carry_create", "pg_carry_reset", "pg_carry_destroy", "pg_env_step_single",
+           "pg_dyn_feasible_qp", "pg_dyn_sweep_qp", "pg_carry_create", "pg_carry_reset", "pg_carry_destroy", "pg_env_step_single", "pg_set_rollout_mode",
            "pg_launch_count")
 
 

@@ -25,6 +25,11 @@ using namespace pg;
 extern "C" const char* pg_last_error(void) { return g_err.c_str(); }
 extern "C" const char* pg_version(void) { return "pregrasp_b200 0.1 (sm_100a)"; }
 extern "C" uint64_t pg_launch_count(void) { return g_launches.load(); }
+extern "C" int pg_set_rollout_mode(PgEnv* e, int mode) {
+  if (!e || mode < 0 || mode > 2) { set_error("pg_set_rollout_mode: bad arguments"); return PG_ERR_INVALID; }
+  e->rollout_mode = mode;
+  return PG_OK;
+}
 
 
 static void pk_quat_to_matrix(const double* q_xyzw, double* R) {
@@ -192,7 +197,7 @@ extern "C" int pg_env_destroy(PgEnv* e) {
   cudaSetDevice(e->device);
   cudaFree(e->blob); cudaFree(e->pose); cudaFree(e->fins); cudaFree(e->logit); cudaFree(e->latent); cudaFree(e->path_dev);
   cudaFree(e->u_stage); cudaFree(e->noise_stage); cudaFree(e->J_stage); cudaFree(e->metric_stage); cudaFree(e->trace_stage);
-  cudaFree(e->regroup);
+  cudaFree(e->regroup); cudaFree(e->ph_states); cudaFree(e->ph_order); cudaFree(e->ph_hist);
   if (e->host_stream) cudaStreamDestroy(e->host_stream);
   delete e;
   return PG_OK;

@@ -68,6 +68,9 @@ struct PgEnv {
   size_t cap_stage_K, cap_stage_trace;
   cudaStream_t host_stream;            // pg_rollout_host: copies + kernels of one handle run on its own stream
   void* regroup; size_t cap_regroup;   // settle-phase exchange buffer of the rollout kernel ([K] RegroupSlot)
+  void* ph_states; size_t cap_ph;      // phased rollouts: [K] RolloutState between phases, sort scratch
+  int *ph_order, *ph_hist;
+  int rollout_mode;                    // 0 auto (phased for large batches), 1 persistent kernel, 2 phased (pg_set_rollout_mode)
 };
 
 namespace pg {
@@ -78,6 +81,8 @@ void count_launch();
 int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
                    double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st,
                    const int* prob_dev = nullptr);
+int launch_physics_phased(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
+                          double* pose, double* fins, double* metric, cudaStream_t st, const int* prob_dev);
 size_t episode_state_bytes();
 int launch_episode(PgEnv* env, void* state, const double* a, int cstate, double max_force, int settle, double* pose7, double* fins6,
                    double* metric, double* trace, cudaStream_t st);

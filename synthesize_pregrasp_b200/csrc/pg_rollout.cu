@@ -38,6 +38,12 @@ int launch_episode(PgEnv* env, void* state, const double* a, int cstate, double 
 
 int launch_physics(PgEnv* env, const double* u, const float* noise, int K, int N, const int* path_dev, double max_force,
                    double* pose, double* fins, double* metric, double* trace, int* iters, cudaStream_t st, const int* prob_dev) {
+  // The measured alternative (pg_rollout_phase.cuh): one launch per episode phase with the rollouts re-sorted by solver work in
+  // between.  Bit-identical results; on the B200 it is 11-40 % SLOWER than the persistent kernel below (profiles/README.md), so it
+  // runs only when asked for (pg_set_rollout_mode(env, 2)).
+  const bool phased = env->rollout_mode == 2;
+  if (phased && !trace && !iters)
+    return launch_physics_phased(env, u, noise, K, N, path_dev, max_force, pose, fins, metric, st, prob_dev);
   // exchange buffer of the settle-phase regrouping (pg_rollout.cuh), one slot per rollout
   const size_t need = (size_t)K * sizeof(RegroupSlot);
   if (env->cap_regroup < need) {

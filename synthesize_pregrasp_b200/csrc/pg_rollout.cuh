@@ -216,11 +216,12 @@ PG_HD void env_reset(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, Carry
   for (int f = 0; f < NFING; f++) { carry.on[f] = 0; carry.pos[f] = V3(); carry.norm[f] = V3(); }
 }
 
-// ---- step(a): plate_env:253-632 for env step j of the episode (a = the raw action, before tanh).  `settle`: the train-mode
-// settle + metric of the last step (:556-603).  Writes out.fins / out.pose row j (+ trace / iters rows of this step).
+// ---- step(a), control part: plate_env:253-555 for env step j of the episode (a = the raw action, before tanh): decode,
+// pre_simulate, the 50 servo substeps.  Writes out.fins row j (+ trace / iters rows of this step); returns the solver work of
+// the servo phase (the key the rollouts are re-dealt / sorted by).
 template <int SHAPE>
-PG_HD void env_step(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, Carry& carry, const double* a, int state, int prev_state,
-                    double max_force, bool settle, int j, RolloutOut& out, double* sm, int ss) {
+PG_HD int env_control(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, Carry& carry, const double* a, int state, int prev_state,
+                      double max_force, int j, RolloutOut& out, double* sm, int ss) {
   V3 cur_pos[NFING];
   int cur_on[NFING];
   double knots[NFING][NKNOT][3];
@@ -266,42 +267,47 @@ PG_HD void env_step(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, Carry&
 #if !defined(PG_PHASE_CLOCKS)
     if (out.iters) out.iters[j * SKIP + t] = S.last_iterations;
 #endif
-#if defined(PG_REGROUP_EVERY)
     solver_work += S.last_iterations * (12 + 2 * rs.n_pts);    // sweeps x rows
-#else
-    solver_work += S.last_iterations;
-#endif
   }
   for (int i = 0; i < NFING; i++) {
     out.fins[(j * NFING + i) * 3 + 0] = cur_pos[i].x;
     out.fins[(j * NFING + i) * 3 + 1] = cur_pos[i].y;
     out.fins[(j * NFING + i) * 3 + 2] = cur_pos[i].z;
   }
-  // ---- settle + metric :556-603 (train mode)
+  return solver_work;
+}
+
+PG_HD void write_pose(const Sim& S, double* p) {
+  const DynBody& o = S.dyn[0];
+  p[0] = o.pos.x; p[1] = o.pos.y; p[2] = o.pos.z; p[3] = o.q.x; p[4] = o.q.y; p[5] = o.q.z; p[6] = o.q.w;
+}
+
+// first half of the settle metric (plate_env:558): the object's height / depth before the settle substeps
+PG_HD double settle_metric_half(const EnvDev& E, const Sim& S) { return (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5; }
+
+// ---- step(a) = control part + (last step, train mode) settle + metric :556-603, then the pose the cost is evaluated at
+template <int SHAPE>
+PG_HD void env_step(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, Carry& carry, const double* a, int state, int prev_state,
+                    double max_force, bool settle, int j, RolloutOut& out, double* sm, int ss) {
+  int solver_work = env_control<SHAPE>(E, S, statR, rs, carry, a, state, prev_state, max_force, j, out, sm, ss);
   if (settle) {
-    double m0 = (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
+    double m0 = settle_metric_half(E, S);
 #if defined(__CUDA_ARCH__)
     if (out.regroup) settle_regroup(S, m0, out, solver_work);     // from here on this thread may run another rollout of its CTA
 #endif
-#if defined(PG_REGROUP_EVERY)
     int recent_work = 0;                              // solver work since the last re-deal
-#endif
     for (int s = 0; s < E.settle_substeps; s++) {
 #if defined(__CUDA_ARCH__) && defined(PG_REGROUP_EVERY)
       // the kind of a rollout drifts while it settles: re-deal again every PG_REGROUP_EVERY substeps by the work just seen
       if (out.regroup && s > 0 && s % PG_REGROUP_EVERY == 0) { settle_regroup(S, m0, out, recent_work); recent_work = 0; }
 #endif
       substep<SHAPE>(E, S, statR, rs, sm, ss);
-#if defined(PG_REGROUP_EVERY)
       recent_work += S.last_iterations * (12 + 2 * rs.n_pts);
-#endif
       if (out.settle_iters) out.settle_iters[s] = S.last_iterations;
     }
-    if (out.metric) *out.metric = m0 + (S.dyn[0].pos[E.metric_axis] + E.metric_offset) * 0.5;
+    if (out.metric) *out.metric = m0 + settle_metric_half(E, S);
   }
-  DynBody& o = S.dyn[0];
-  double* p = out.pose + j * 7;
-  p[0] = o.pos.x; p[1] = o.pos.y; p[2] = o.pos.z; p[3] = o.q.x; p[4] = o.q.y; p[5] = o.q.z; p[6] = o.q.w;
+  write_pose(S, out.pose + j * 7);
 }
 
 PG_HD void static_rotations(const EnvDev& E, M3* statR) {

@@ -47,6 +47,10 @@ class RolloutEngine:
         _abi.check(self.lib.pg_env_create(C.byref(cspec), self.device, C.byref(h)))
         self.handle = h
 
+    def set_rollout_mode(self, mode: int):
+        """0 auto, 1 persistent one-launch kernel, 2 phased with work-sorted rollouts (pg_set_rollout_mode); same results."""
+        _abi.check(self.lib.pg_set_rollout_mode(self.handle, int(mode)))
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.pg_env_destroy(self.handle)

@@ -281,6 +281,38 @@ def test_env_step_single_matches_batch_trace(EN, exp):
         env.step(g["u"][1])
 
 
+@pytest.mark.parametrize("env,F", [("bookshelf", 50.0), ("plate", 20.0)])
+def test_phased_sorted_rollouts_equal_persistent_kernel(EN, env, F):
+    """pg_set_rollout_mode: the phased path (one launch per episode phase, rollouts re-sorted by solver work in between, state in
+    global memory) and the persistent one-launch kernel run the same per-rollout code -- poses, fingertip points, metric and
+    costs must be bit-identical, also for a batch that leaves a partly filled CTA and for several problems in one launch."""
+    from synthesize_pregrasp_b200.envspec import make_spec
+    eng = EN.RolloutEngine(make_spec(env), device=0)
+    K, N = 600, 2
+    gen = torch.Generator(device="cuda:0").manual_seed(4242)
+    noise = 0.8 * torch.randn((K, N, 48), generator=gen, device="cuda:0", dtype=torch.float32)
+    u = 0.1 * np.random.RandomState(3).randn(N, 48)
+    res = {}
+    for mode in (1, 2):
+        eng.set_rollout_mode(mode)
+        out = eng.physics(u, noise, [0, 0], F)
+        J, metric = eng.rollout(u, noise, [0, 0], F, want_metric=True)
+        res[mode] = [out["pose"].cpu().numpy(), out["fins"].cpu().numpy(), out["metric"].cpu().numpy(), J.cpu().numpy(), metric.cpu().numpy()]
+    for a, b in zip(res[1], res[2]):
+        assert np.array_equal(a, b, equal_nan=True)
+    # several MPPI problems in one launch (pg_rollout_multi) through the phased path
+    Q = 3
+    uQ = torch.as_tensor(0.1 * np.random.RandomState(4).randn(Q, N, 48), device="cuda:0")
+    prob = torch.arange(Q, dtype=torch.int32, device="cuda:0").repeat_interleave(K // Q).contiguous()
+    paths = np.zeros((Q, N), np.int32)
+    Jm = {}
+    for mode in (1, 2):
+        eng.set_rollout_mode(mode)
+        Jm[mode] = eng.rollout_multi(uQ, noise, prob, paths, F).cpu().numpy()
+    assert np.array_equal(Jm[1], Jm[2], equal_nan=True)
+    eng.set_rollout_mode(0)
+
+
 def test_mppi_update_kernel(EN):
     from oracle import mppi
     m = np.load(os.path.join(G, "mppi_update.npz"))

@@ -1,7 +1,12 @@
 #!/bin/bash
-# N-GPU weak-scaling run of bench.py (torchrun, NCCL); N from $1
-N=${1:-2}
+# Multi-GPU lines of round 2 (one box, N = $1 GPUs):  gpurun --gpus N -- 'bash tools/gpu_scale.sh N'
+N=$1
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/scale_gpus.txt
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 --cpu-sample 2 > gpurun_out/scale_n$N.log 2>&1
-tail -1 gpurun_out/scale_n$N.log | cut -c1-400
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+run() { name=$1; shift; timeout 900 $TR bench.py --gpus $N "$@" > gpurun_out/r2_scale_n${N}_$name.json 2> gpurun_out/r2_scale_n${N}_$name.err; tail -c 700 gpurun_out/r2_scale_n${N}_$name.json; echo; tail -2 gpurun_out/r2_scale_n${N}_$name.err; }
+run bookshelf_K65536 --steps 3 --warmup 3 --no-extra --cpu-sample 16
+run waterbottle_K1048576 --workload waterbottle_K1048576 --steps 1 --warmup 1 --cpu-sample 8
+if [ "$N" = 8 ]; then
+  run dyn_sweep_P1024 --workload dyn_sweep_P1024 --steps 2 --warmup 1
+  run multi_env --workload multi_env --steps 2 --warmup 1
+fi
