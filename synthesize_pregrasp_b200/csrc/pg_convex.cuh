@@ -5,6 +5,8 @@
 //   * core distance below 1 mm or overlapping cores: expanding-polytope penetration query on the margin-inclusive
 //     shapes, nine guess directions
 // Index-based pools and explicit stacks (no recursion, no pointers) so one thread can run it out of local memory.
+// Written after bullet3's published btGjkPairDetector / btVoronoiSimplexSolver / btGjkEpa2 (zlib licence, (c) Erwin Coumans,
+// Nathanael Presson et al.): bit-level parity with that engine requires its thresholds and operation order.
 #pragma once
 #include "pg_math.cuh"
 

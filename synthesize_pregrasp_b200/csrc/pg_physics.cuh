@@ -9,6 +9,10 @@
 // manifolds, fixed-iteration projected Gauss-Seidel (fingertip servo rows in alternating order, normal
 // rows, paired cone-friction rows, residual early-out), semi-implicit Euler with exponential-map
 // orientation update, dt = 1/250 s.  fp64 throughout: contact-rich rollouts amplify rounding.
+// The box-box detector (box_box, rect_quad, cull_points, line_closest), the persistent-manifold rules (cache_entry, sort_cached,
+// refresh) and the solver row order are written after bullet3's published btBoxBoxDetector / btPersistentManifold /
+// btSequentialImpulseConstraintSolver (zlib licence, (c) Erwin Coumans et al.; btBoxBoxDetector after ODE's dBoxBox2, (c) Russell
+// L. Smith): bit-level parity with that engine requires its operation order.
 #pragma once
 #include "pg_env.cuh"
 #include "pg_convex.cuh"
