@@ -6,8 +6,8 @@
 //   h1  = relu(conv1)                                   CUDA cores (4 -> 32: xyz part precomputed per point, + w1d * df)
 //   D2  = h1 . W2^T                 [128x32].[32x64]    tcgen05   -> global max-pool g (pass 1 over the cloud)
 //   D3  = h1 . (W3a W2)^T           [128x32].[32x256]   tcgen05   conv3's point half with conv2 folded in:  W3a (W2 h1 + b2)
-//   z   = relu(D3 + c),  c = b3 + W3a b2 + W3b g        epilogue on the TMEM rows; z is written straight back to shared
-//                                                       memory as the A operand of the next GEMM (back-to-back fusion)
+//   z   = relu(D3 + c),  c = b3 + W3a b2 + W3b g        epilogue on the TMEM rows; z is written straight back to TENSOR
+//                                                       MEMORY as the A operand of the next GEMM (back-to-back fusion)
 //   D4  = z . W4^T                  [128x256].[256x32]  tcgen05   (20 outputs padded to N = 32), accumulated over 8 K-chunks
 //   lat = masked max over points of D4 + b4
 // so all of the network's point-wise FLOPs (the ones SURVEY 8(d) counts: 164.1 MFLOP per evaluation) run on the tensor cores;
@@ -15,9 +15,10 @@
 // fp32 fidelity on tf32 tensor cores: both operands are split a = a_hi + a_lo (a_hi = cvt.rna.tf32, a_lo = a - a_hi
 // exactly) and three MMAs a_hi*b_hi + a_hi*b_lo + a_lo*b_hi accumulate into the same TMEM tile (dropped term
 // a_lo*b_lo <= 2^-22 relative), because MPPI weights exp(-5*100*dlogit) do not tolerate plain-tf32 logits.
-// Operands sit in shared memory in the no-swizzle K-major canonical layout ([k-chunk of 16 B][row][16 B]:
-// SBO = 128 B between 8-row groups, LBO = rows*16 B between the two 16-byte halves of one K=8 step).  The weight operands
-// (hi / lo, already in that layout) are brought in once per CTA by TMA bulk copies (cp.async.bulk -> mbarrier).
+// A operands (h1 tiles, z chunks) live in tensor memory (tcgen05.st by the producer warps, tcgen05.mma with [a_tmem]); the weight
+// operands sit in shared memory in the no-swizzle K-major canonical layout ([k-chunk of 16 B][row][16 B]: SBO = 128 B between
+// 8-row groups, LBO = rows*16 B between the two 16-byte halves of one K=8 step), hi / lo already in that layout, brought in once
+// per CTA by TMA bulk copies (cp.async.bulk -> mbarrier).
 #include "pg_internal.h"
 #include "pg_cost_geom.cuh"
 
@@ -34,24 +35,13 @@ namespace pg {
 #define TC_W2 (C2 / TC_NG)               // conv2 channels reduced per thread (pass 1)
 #define TC_WC (TC_KC / TC_NG)            // z channels per thread and K-chunk
 #define TC_W4 (TC_N4 / TC_NG)            // conv4 outputs per thread
-#ifdef TC_ABLATE_PASS1
-#define TC_P1_TILES(T) 0
-#else
-#define TC_P1_TILES(T) (T)
-#endif
-#ifdef TC_ABLATE_CHUNKS
-#define TC_NCHUNK 0
-#else
-#define TC_NCHUNK (C3 / TC_KC)
-#endif
+#define TC_NB 3                          // A-operand buffers in tensor memory (64 columns each: 32 hi + 32 lo)
 #define TC_NT (TC_THREADS + 32)           // + one warp whose lane 0 issues every tcgen05.mma
 
 struct TcSmem {
   float w32_hi[C1 * C3], w32_lo[C1 * C3];   // (W3a W2)  [256 x 32]  canonical K-major: [(k/4)][n][k%4]
   float w4_hi[C3 * TC_N4], w4_lo[C3 * TC_N4];   // W4 (padded) [32 x 256]
   float w2_hi[C1 * C2], w2_lo[C1 * C2];     // W2        [64 x 32]
-  float a1_hi[C1 * TC_M], a1_lo[C1 * TC_M]; // h1 tile   [128 x 32]  [(k/4)][row][k%4]
-  float a4_hi[TC_KC * TC_M], a4_lo[TC_KC * TC_M];   // z chunk [128 x 32]
   float df[P_CLOUD];
   float c[C3];
   float g[C2];
@@ -60,7 +50,7 @@ struct TcSmem {
   float lat[LAT + 2];
   double pose[7], R[9], fin[6];
   unsigned char msk[P_CLOUD];
-  unsigned long long mbar_w, full[2], done[2];   // weights landed | operand buffer b written by the 8 producer warps | MMAs reading buffer b complete
+  unsigned long long mbar_w, full[TC_NB], done[TC_NB];   // weights landed | A buffer b written by all producer warps | MMAs reading buffer b complete
   unsigned int tmem_base;
   int count;
 };
@@ -86,17 +76,19 @@ __device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// tcgen05.mma with the A operand in TENSOR MEMORY (lane = row, one tf32 per 32-bit column) and B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 
 // D[128 x N] (+)= A[128 x K] . B[N x K]^T with the 3x-split: per K = 8 step  a_hi b_hi + a_hi b_lo + a_lo b_hi.
-// A: rows = TC_M, B: rows = N, both canonical K-major; issued by ONE thread, which is the critical path of every step that
-// waits for the tensor core -- so the four operand descriptors are built ONCE (desc_* below) and a K step only advances their
-// 14-bit start-address field (address >> 4; the operands stay far below the field's 256 KB range, so the add never carries).
+// A: tensor memory, hi part in columns [a, a + K), lo part in [a + 32, a + 32 + K) (written by the producers with tcgen05.st: the
+// operand never touches shared memory, no proxy fence, and the MMA's A read leaves the shared-memory bandwidth to B).
+// B: rows = N, canonical K-major in shared memory.  Issued by ONE thread, which is on the critical path of every hand-off: the B
+// descriptors are built once (OpDesc) and a K step only advances their 14-bit start-address field (address >> 4).
 struct OpDesc { uint64_t hi, lo; };                                   // descriptors of the hi / lo part of one operand at K step 0
 template <int ROWS>
 __device__ __forceinline__ OpDesc make_opdesc(uint32_t hi_addr, uint32_t lo_addr) {
@@ -106,14 +98,14 @@ __device__ __forceinline__ OpDesc make_opdesc(uint32_t hi_addr, uint32_t lo_addr
   return d;
 }
 template <int N, int K>
-__device__ __forceinline__ void gemm_split3(uint32_t tmem_d, OpDesc a, OpDesc b, uint32_t accumulate) {
+__device__ __forceinline__ void gemm_split3(uint32_t tmem_d, uint32_t tmem_a, OpDesc b, uint32_t accumulate) {
   constexpr uint32_t idesc = make_idesc(N);
-  constexpr uint64_t step_a = (2u * TC_M * 16u) >> 4, step_b = (2u * N * 16u) >> 4;   // one K = 8 step = two 16-byte chunks
+  constexpr uint64_t step_b = (2u * N * 16u) >> 4;                    // one K = 8 step = two 16-byte chunks of B
 #pragma unroll
   for (int ks = 0; ks < K / 8; ks++) {
-    mma_tf32(tmem_d, a.hi + ks * step_a, b.hi + ks * step_b, idesc, (ks > 0 || accumulate) ? 1u : 0u);
-    mma_tf32(tmem_d, a.hi + ks * step_a, b.lo + ks * step_b, idesc, 1u);
-    mma_tf32(tmem_d, a.lo + ks * step_a, b.hi + ks * step_b, idesc, 1u);
+    mma_tf32_ts(tmem_d, tmem_a + 8 * ks, b.hi + ks * step_b, idesc, (ks > 0 || accumulate) ? 1u : 0u);
+    mma_tf32_ts(tmem_d, tmem_a + 8 * ks, b.lo + ks * step_b, idesc, 1u);
+    mma_tf32_ts(tmem_d, tmem_a + 32 + 8 * ks, b.hi + ks * step_b, idesc, 1u);
   }
 }
 
@@ -124,12 +116,10 @@ __device__ __forceinline__ void mma_commit(uint32_t mbar) {
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(mbar) : "memory");
 }
-// a producer warp publishes its part of an operand buffer: generic-proxy stores -> async proxy, order the warp's TMEM reads,
-// then one arrival per warp (the barriers count the producer warps)
+// a producer warp publishes its part of an A buffer: its tcgen05.st have completed, its TMEM reads are ordered, then one arrival
+// per warp (the barriers count the producer warps)
 __device__ __forceinline__ void publish(uint32_t mbar, int lane) {
-#if !defined(TC_ABLATE_FENCE)
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncwarp();
   if (lane == 0) mbar_arrive(mbar);
@@ -161,6 +151,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 template <int W> __device__ __forceinline__ void tc_ld(uint32_t* v, uint32_t taddr) {
   if (W == 16) { TC_LD16(v, taddr); } else { TC_LD8(v, taddr); }
 }
+#define TC_ST8(taddr, v)                                                                                                        \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"                                   \
+               :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory")
 #define TC_LD_WAIT() asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
 
 __device__ __forceinline__ float tc_box_dist(double x, double y, double z, const double* lo, const double* hi) {
@@ -171,25 +164,30 @@ __device__ __forceinline__ float tc_box_dist(double x, double y, double z, const
   return (float)(outside > 0 ? outside : fmax(inside, 0.0));
 }
 
-// conv1 + ReLU for TC_W1 of the 32 channels of point p (thread (row, grp): channels TC_W1 grp ..), split into tf32 hi / lo and
-// stored as the A operand of the next GEMM; rows beyond the cloud are zero
-__device__ __forceinline__ void stage_h1(TcSmem& s, const CostDev& cd, int p, int P, int row, int grp, float* dst_hi, float* dst_lo) {
+// conv1 + ReLU for TC_W1 = 8 of the 32 channels of point p (thread (row, grp): channels 8 grp ..), split into tf32 hi / lo and
+// stored into A buffer `abuf` (tensor memory, this thread's lane: hi in columns 8 grp .., lo 32 columns further); rows beyond the
+// cloud are zero
+__device__ __forceinline__ void stage_h1(const TcSmem& s, const CostDev& cd, int p, int P, int grp, uint32_t abuf_lane) {
+  static_assert(TC_W1 == 8, "one x8 tensor-memory store per half");
+  uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int q = 0; q < TC_W1 / 4; q++) {
-    const int j = TC_W1 * grp + 4 * q;
-    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+  for (int q = 0; q < 2; q++) {
+    const int j = 8 * grp + 4 * q;
+    float h[4] = {0.f, 0.f, 0.f, 0.f};
     if (p < P) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(cd.a1 + (size_t)p * C1 + j));
       const float df = s.df[p];
-      const float h0 = fmaxf(fmaf(s.w1d[j], df, v.x), 0.f), h1 = fmaxf(fmaf(s.w1d[j + 1], df, v.y), 0.f);
-      const float h2 = fmaxf(fmaf(s.w1d[j + 2], df, v.z), 0.f), h3 = fmaxf(fmaf(s.w1d[j + 3], df, v.w), 0.f);
-      hi = make_float4(tf32_rna(h0), tf32_rna(h1), tf32_rna(h2), tf32_rna(h3));
-      lo = make_float4(h0 - hi.x, h1 - hi.y, h2 - hi.z, h3 - hi.w);
+      h[0] = fmaxf(fmaf(s.w1d[j], df, v.x), 0.f); h[1] = fmaxf(fmaf(s.w1d[j + 1], df, v.y), 0.f);
+      h[2] = fmaxf(fmaf(s.w1d[j + 2], df, v.z), 0.f); h[3] = fmaxf(fmaf(s.w1d[j + 3], df, v.w), 0.f);
     }
-    const int o = ((j >> 2) * TC_M + row) * 4;
-    *reinterpret_cast<float4*>(dst_hi + o) = hi;
-    *reinterpret_cast<float4*>(dst_lo + o) = lo;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float hh = tf32_rna(h[i]);
+      hi[4 * q + i] = __float_as_uint(hh); lo[4 * q + i] = __float_as_uint(h[i] - hh);
+    }
   }
+  TC_ST8(abuf_lane + (uint32_t)(8 * grp), hi);
+  TC_ST8(abuf_lane + (uint32_t)(32 + 8 * grp), lo);
 }
 
 __global__ void __launch_bounds__(TC_NT, 1)
@@ -201,7 +199,7 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
   const bool issuer = warp == TC_THREADS / 32;             // the extra warp: lane 0 issues the MMAs, never touches operands or TMEM data
   const int P = cd.n_cloud;
   const uint32_t mbar_w = smem_u32(&s.mbar_w);
-  const uint32_t full0 = smem_u32(&s.full[0]), full1 = smem_u32(&s.full[1]), done0 = smem_u32(&s.done[0]), done1 = smem_u32(&s.done[1]);
+  const uint32_t full_b = smem_u32(&s.full[0]), done_b = smem_u32(&s.done[0]);     // barrier b at + 8 b
 
   // ---- one-time setup: TMEM allocation, mbarriers, weight operands by TMA bulk copies
   if (warp == 0) {
@@ -210,10 +208,10 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
   }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar_w));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(full0), "n"(TC_THREADS / 32));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(full1), "n"(TC_THREADS / 32));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(done0));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(done1));
+    for (int b = 0; b < TC_NB; b++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(full_b + 8 * b), "n"(TC_THREADS / 32));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(done_b + 8 * b));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;");
     const uint32_t bytes = 4u * (2 * C1 * C3 + 2 * C3 * TC_N4 + 2 * C1 * C2);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_w), "r"(bytes) : "memory");
@@ -229,15 +227,17 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
   asm volatile("tcgen05.fence::after_thread_sync;");
   mbar_wait(mbar_w, 0);                                    // weights landed (async proxy writes, visible to the tensor core)
   const uint32_t tmem = s.tmem_base;
-  const uint32_t tm_d3 = tmem, tm_d4 = tmem + C3, tm_d2 = tmem;          // D3: columns 0..255, D4: 256..287, D2[0|1] (pass 1) alias D3
+  // tensor-memory map (512 columns): D3 0..255 | D4 256..287 | A buffers 288 + 64 b (32 hi + 32 lo columns each); pass 1: D2[0|1] alias D3
+  const uint32_t tm_d3 = tmem, tm_d4 = tmem + C3, tm_d2 = tmem, tm_a = tmem + C3 + TC_N4;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-  const OpDesc d_a1 = make_opdesc<TC_M>(smem_u32(s.a1_hi), smem_u32(s.a1_lo)), d_a4 = make_opdesc<TC_M>(smem_u32(s.a4_hi), smem_u32(s.a4_lo));
   const OpDesc d_w32 = make_opdesc<C3>(smem_u32(s.w32_hi), smem_u32(s.w32_lo)), d_w2 = make_opdesc<C2>(smem_u32(s.w2_hi), smem_u32(s.w2_lo));
   const OpDesc d_w4 = make_opdesc<TC_N4>(smem_u32(s.w4_hi), smem_u32(s.w4_lo));
-  // Producer / consumer protocol.  Operand buffer 0 = a4, buffer 1 = a1.  full[b]: the 8 producer warps have written buffer b
-  // (one arrival per warp); done[b]: the MMAs that read buffer b have completed (tcgen05.commit by the issuer).  Each side keeps
-  // the parities of the barriers it waits on; both walk the same sequence of tiles / K-chunks.
-  uint32_t pf0 = 0, pf1 = 0, pd0 = 0, pd1 = 0;
+  // Producer / consumer protocol.  full[b]: every producer warp has written A buffer b (one arrival per warp); done[b]: the MMAs
+  // that read buffer b have completed (tcgen05.commit by the issuer).  Each side keeps the parities of the barriers it waits on
+  // (bit b of pf / pd); both walk the same sequence of tiles / K-chunks.
+  uint32_t pf = 0, pd = 0;
+#define TC_WAIT_FULL(b) { mbar_wait(full_b + 8 * (b), (pf >> (b)) & 1u); pf ^= 1u << (b); }
+#define TC_WAIT_DONE(b) { mbar_wait(done_b + 8 * (b), (pd >> (b)) & 1u); pd ^= 1u << (b); }
   const int T = (P + TC_M - 1) / TC_M;
 
   for (int e = blockIdx.x; e < B; e += gridDim.x) {
@@ -254,12 +254,7 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
     }
     __syncthreads();
     int cnt = 0;
-#if defined(TC_ABLATE_GEOM)
-    for (int p = tid; p < P; p += TC_NT) { s.df[p] = 0.01f; s.msk[p] = 1; cnt++; }
-    for (int p = tid; p < 0; p += TC_NT) {
-#else
     for (int p = tid; p < P; p += TC_NT) {
-#endif
       double cx = cd.cloud[3 * p], cy = cd.cloud[3 * p + 1], cz = cd.cloud[3 * p + 2];
       double wx = s.R[0] * cx + s.R[1] * cy + s.R[2] * cz + s.pose[0];
       double wy = s.R[3] * cx + s.R[4] * cy + s.R[5] * cz + s.pose[1];
@@ -333,34 +328,30 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
     }
 
     if (issuer) {
-      // ================= MMA issuer (one thread): waits for operand buffers, feeds the tensor core, signals completion
+      // ================= MMA issuer (one thread): waits for A buffers, feeds the tensor core, signals completion
       if (lane == 0) {
-        for (int t = 0; t < TC_P1_TILES(T); t++) {                                  // pass 1: D2[t & 1] = h1 tile . W2^T
+        for (int t = 0; t < T; t++) {                                  // pass 1: D2[t & 1] = h1 tile . W2^T, A buffer t & 1
           const int b = t & 1;
-          if (b) { mbar_wait(full1, pf1); pf1 ^= 1; } else { mbar_wait(full0, pf0); pf0 ^= 1; }
+          TC_WAIT_FULL(b);
           asm volatile("tcgen05.fence::after_thread_sync;");
-          gemm_split3<C2, C1>(tm_d2 + (uint32_t)(b * C2), b ? d_a1 : d_a4, d_w2, 0u);
-          mma_commit(b ? done1 : done0);
+          gemm_split3<C2, C1>(tm_d2 + (uint32_t)(b * C2), tm_a + 64u * b, d_w2, 0u);
+          mma_commit(done_b + 8 * b);
         }
         for (int t = 0; t < T; t++) {                                  // pass 2
-          mbar_wait(full1, pf1); pf1 ^= 1;
+          TC_WAIT_FULL(2);
           asm volatile("tcgen05.fence::after_thread_sync;");
-#if !defined(TC_ABLATE_MMA3)
-          gemm_split3<C3, C1>(tm_d3, d_a1, d_w32, 0u);                 // D3 = h1 tile . (W3a W2)^T
-#endif
-          mma_commit(done1);
+          gemm_split3<C3, C1>(tm_d3, tm_a + 128u, d_w32, 0u);          // D3 = h1 tile (A buffer 2) . (W3a W2)^T
+          mma_commit(done_b + 16);
 #pragma unroll 1
-          for (int ch = 0; ch < TC_NCHUNK; ch++) {                    // D4 += z chunk . W4 chunk^T
-            const int b = ch & 1;
-            if (b) { mbar_wait(full1, pf1); pf1 ^= 1; } else { mbar_wait(full0, pf0); pf0 ^= 1; }
+          for (int ch = 0; ch < C3 / TC_KC; ch++) {                    // D4 += z chunk (A buffer ch % 3) . W4 chunk^T
+            const int b = ch % TC_NB;
+            TC_WAIT_FULL(b);
             asm volatile("tcgen05.fence::after_thread_sync;");
             // W4 chunk: K rows 32 ch .. of the [32 x 256] operand = byte offset (32 ch / 4) * (N * 16), in descriptor units (>> 4)
             const uint64_t boff = (uint64_t)((TC_KC * ch / 4) * (TC_N4 * 16) >> 4);
             OpDesc w4c; w4c.hi = d_w4.hi + boff; w4c.lo = d_w4.lo + boff;
-#if !defined(TC_ABLATE_MMA4)
-            gemm_split3<TC_N4, TC_KC>(tm_d4, b ? d_a1 : d_a4, w4c, ch > 0 ? 1u : 0u);
-#endif
-            mma_commit(b ? done1 : done0);
+            gemm_split3<TC_N4, TC_KC>(tm_d4, tm_a + 64u * b, w4c, ch > 0 ? 1u : 0u);
+            mma_commit(done_b + 8 * b);
           }
         }
       }
@@ -368,21 +359,19 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
     } else {
       // ================= producers / epilogue (TC_NG warps per TMEM lane quadrant; thread (row, grp))
       // ---------------- pass 1: g = masked max over points of conv2 (N = 64); this thread: channels TC_W2 grp .. of its row.
-      // Software pipeline over the tiles: tile t + 1 is staged (other buffer, other accumulator region) before tile t is reduced.
+      // Software pipeline over the tiles: tile t + 1 is staged (other A buffer, other accumulator region) before tile t is reduced.
       float gmax[TC_W2];
 #pragma unroll
       for (int c = 0; c < TC_W2; c++) gmax[c] = -INFINITY;
-#if !defined(TC_ABLATE_PASS1)
-      stage_h1(s, cd, row, P, row, grp, s.a4_hi, s.a4_lo);
-      publish(full0, lane);
-#endif
-      for (int t = 0; t < TC_P1_TILES(T); t++) {
+      stage_h1(s, cd, row, P, grp, tm_a + lane_base);
+      publish(full_b, lane);
+      for (int t = 0; t < T; t++) {
         const int b = t & 1;
-        if (t + 1 < T) {                 // buffer 1 - b / D2[1 - b] were released when this thread finished tile t - 1
-          stage_h1(s, cd, (t + 1) * TC_M + row, P, row, grp, b ? s.a4_hi : s.a1_hi, b ? s.a4_lo : s.a1_lo);
-          publish(b ? full0 : full1, lane);
+        if (t + 1 < T) {                 // A buffer 1 - b / D2[1 - b] were released when this thread finished tile t - 1
+          stage_h1(s, cd, (t + 1) * TC_M + row, P, grp, tm_a + 64u * (1 - b) + lane_base);
+          publish(full_b + 8 * (1 - b), lane);
         }
-        if (b) { mbar_wait(done1, pd1); pd1 ^= 1; } else { mbar_wait(done0, pd0); pd0 ^= 1; }
+        TC_WAIT_DONE(b);
         asm volatile("tcgen05.fence::after_thread_sync;");
         const int p = t * TC_M + row;
         const bool keep = p < P && s.msk[p];
@@ -435,50 +424,39 @@ pcn_tc_kernel(CostDev cd, TcWeights tw, const double* __restrict__ pose, const d
       for (int o = 0; o < TC_W4; o++) rmax[o] = -INFINITY;
       for (int t = 0; t < T; t++) {
         const int p = t * TC_M + row;
-        stage_h1(s, cd, p, P, row, grp, s.a1_hi, s.a1_lo);           // a1 is free: its last reader (chunk 7 of the previous tile) was waited for
-        publish(full1, lane);
-        mbar_wait(done1, pd1); pd1 ^= 1;                               // D3 complete
+        stage_h1(s, cd, p, P, grp, tm_a + 128u + lane_base);          // A buffer 2 is free: its last reader (chunk 5 of the previous tile) was waited for
+        publish(full_b + 16, lane);
+        TC_WAIT_DONE(2);                                               // D3 complete
         asm volatile("tcgen05.fence::after_thread_sync;");
-        // back-to-back: z chunk ch (channels 32 ch ..) = relu(D3 + c) -> shared memory (tf32 hi / lo) -> D4 += z_chunk . W4_chunk^T.
-        // Two operand buffers (a4, and a1 -- free once D3 is complete): a buffer is rewritten only after the MMAs of two chunks
-        // earlier have completed; nobody waits for anybody else otherwise.
+        // back-to-back: z chunk ch (channels 32 ch ..) = relu(D3 + c) -> tensor memory (tf32 hi / lo) -> D4 += z_chunk . W4_chunk^T.
+        // Three A buffers in flight: a buffer is rewritten only after the MMAs of three chunks earlier have completed.
 #pragma unroll 1
-        for (int ch = 0; ch < TC_NCHUNK; ch++) {
-          const int b = ch & 1;
+        for (int ch = 0; ch < C3 / TC_KC; ch++) {
+          const int b = ch % TC_NB;
           uint32_t v[TC_WC];
-#if defined(TC_ABLATE_EPI3)
-#pragma unroll
-          for (int i = 0; i < TC_WC; i++) v[i] = 0;
-#else
           tc_ld<TC_WC>(v, tm_d3 + lane_base + (uint32_t)(TC_KC * ch + TC_WC * grp));
           TC_LD_WAIT();
-#endif
-          float4 hi[TC_WC / 4], lo[TC_WC / 4];
+          uint32_t hi[TC_WC], lo[TC_WC];
 #pragma unroll
           for (int q = 0; q < TC_WC / 4; q++) {
             const float4 cc = *reinterpret_cast<const float4*>(s.c + TC_KC * ch + TC_WC * grp + 4 * q);
-            const float z0 = fmaxf(__uint_as_float(v[4 * q]) + cc.x, 0.f), z1 = fmaxf(__uint_as_float(v[4 * q + 1]) + cc.y, 0.f);
-            const float z2 = fmaxf(__uint_as_float(v[4 * q + 2]) + cc.z, 0.f), z3 = fmaxf(__uint_as_float(v[4 * q + 3]) + cc.w, 0.f);
-            hi[q] = make_float4(tf32_rna(z0), tf32_rna(z1), tf32_rna(z2), tf32_rna(z3));
-            lo[q] = make_float4(z0 - hi[q].x, z1 - hi[q].y, z2 - hi[q].z, z3 - hi[q].w);
-          }
-          if (ch >= 2) { if (b) { mbar_wait(done1, pd1); pd1 ^= 1; } else { mbar_wait(done0, pd0); pd0 ^= 1; } }
-          float* dh = b ? s.a1_hi : s.a4_hi;
-          float* dl = b ? s.a1_lo : s.a4_lo;
-#if !defined(TC_ABLATE_EPI3)
+            const float z[4] = {fmaxf(__uint_as_float(v[4 * q]) + cc.x, 0.f), fmaxf(__uint_as_float(v[4 * q + 1]) + cc.y, 0.f),
+                                fmaxf(__uint_as_float(v[4 * q + 2]) + cc.z, 0.f), fmaxf(__uint_as_float(v[4 * q + 3]) + cc.w, 0.f)};
 #pragma unroll
-          for (int q = 0; q < TC_WC / 4; q++) {
-            const int o = (((TC_WC / 4) * grp + q) * TC_M + row) * 4;
-            *reinterpret_cast<float4*>(dh + o) = hi[q];
-            *reinterpret_cast<float4*>(dl + o) = lo[q];
+            for (int i = 0; i < 4; i++) {
+              const float zh = tf32_rna(z[i]);
+              hi[4 * q + i] = __float_as_uint(zh); lo[4 * q + i] = __float_as_uint(z[i] - zh);
+            }
           }
-#endif
-          publish(b ? full1 : full0, lane);
+          if (ch >= TC_NB) TC_WAIT_DONE(b);
+          static_assert(TC_WC == 8, "one x8 tensor-memory store per half");
+          TC_ST8(tm_a + 64u * b + lane_base + (uint32_t)(TC_WC * grp), hi);
+          TC_ST8(tm_a + 64u * b + lane_base + (uint32_t)(32 + TC_WC * grp), lo);
+          publish(full_b + 8 * b, lane);
         }
-#if !defined(TC_ABLATE_CHUNKS)
-        mbar_wait(done0, pd0); pd0 ^= 1;                               // the last two chunks' MMAs
-        mbar_wait(done1, pd1); pd1 ^= 1;
-#endif
+        TC_WAIT_DONE(2);                                               // the last three chunks' MMAs (chunks 5, 6, 7: buffers 2, 0, 1)
+        TC_WAIT_DONE(0);
+        TC_WAIT_DONE(1);
         asm volatile("tcgen05.fence::after_thread_sync;");
         {
           uint32_t v[TC_W4];
