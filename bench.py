@@ -276,6 +276,19 @@ def _lib_sha16():
     return hashlib.sha256(open(_abi.LIB_PATH, "rb").read()).hexdigest()[:16]
 
 
+def _src_sha16():
+    """sha256 over the sources the library is built from (csrc/*.cu, *.cuh, *.h, Makefile): what identifies 'this build' across
+    machines -- nvcc's output is not byte-reproducible, the sources are."""
+    import hashlib
+    d = os.path.join(ROOT, "synthesize_pregrasp_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")) or f == "Makefile":
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "pregrasp_b200.h"), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _fp64_peak():
     """Measured DFMA rate of the box (tools/ubench -> profiles/r2a_ubench.json), else the nominal 148 SM x 64 DFMA/clk."""
     p = os.path.join(ROOT, "profiles", "r2a_ubench.json")
@@ -286,12 +299,12 @@ def _fp64_peak():
 
 def _ncu_traffic(workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE rollout_kernel launch of THIS build (profiles/ncu_traffic.json is
-    written by tools/ncu_traffic.py from a capture of the same library, keyed by the library's sha256); null otherwise."""
+    written by tools/ncu_traffic.py from a capture of the same build, keyed by the sha256 of the library's sources); null otherwise."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return None
     d = json.load(open(p))
-    if d.get("lib_sha16") != _lib_sha16():
+    if d.get("src_sha16") != _src_sha16():
         return None
     return d.get("traffic_bytes", {}).get(workload)
 
@@ -438,7 +451,7 @@ def rollout_line(args, r, world, peaks):
             "note": "algorithmic HBM bytes are ~400 B per rollout-step (u, noise in; pose, fins, metric out), so this fraction is tiny by "
                     "construction: the kernel is bound by instruction issue / dependent-instruction latency of its fp64 code "
                     "(roofline_fp64; ncu evidence in profiles/README.md).  traffic = dram bytes of one launch from an ncu capture of "
-                    "this very build (profiles/ncu_traffic.json, matched by the library's sha256), null when no such capture exists"}
+                    "this very build (profiles/ncu_traffic.json, matched by the sha256 of the library's sources), null when no such capture exists"}
     ach64 = FLOP_PER_SUBSTEP * r["substeps"] * K / (phys_ms * 1e-3) / 1e12
     roof64 = {"kernel": "rollout_kernel", "bound": "fp64-issue", "achieved": ach64, "peak": f64_peak, "unit": "TFLOP/s",
               "frac": ach64 / f64_peak, "peak_source": f64_src, "flop_per_substep": FLOP_PER_SUBSTEP,
@@ -457,7 +470,7 @@ def rollout_line(args, r, world, peaks):
             "stage_ms": {"physics": phys_ms, "cost": cost_ms},
             "roofline": roof, "roofline_fp64": roof64, "roofline_cost": roof_cost, "cpu_baseline": r["cpu_baseline"],
             "e2e": {"value": r["e2e_value"], "unit": "rollout-steps/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
-            "gpu_launches": r["launches"], "clocks": r["clocks"], "host_cores": os.cpu_count() or 1, "lib_sha16": _lib_sha16()}
+            "gpu_launches": r["launches"], "clocks": r["clocks"], "host_cores": os.cpu_count() or 1, "lib_sha16": _lib_sha16(), "src_sha16": _src_sha16()}
 
 
 def _config(workload, env, force, K, path, validate, substeps, l2=None):

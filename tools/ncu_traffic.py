@@ -1,6 +1,6 @@
 """Writes profiles/ncu_traffic.json from an ncu capture of the rollout kernel of THIS build:
-  {"lib_sha16": sha256(libpregrasp_b200.so)[:16], "traffic_bytes": {workload: dram__bytes_read.sum + dram__bytes_write.sum of one launch}}
-bench.py reports roofline.traffic only when the library it times has the same sha (otherwise null).
+  {"src_sha16": sha256 of the library's sources (bench._src_sha16), "traffic_bytes": {workload: dram__bytes_read.sum + dram__bytes_write.sum of one launch}}
+bench.py reports roofline.traffic only when the sources of the library it times have the same sha (otherwise null).
   python tools/ncu_traffic.py <workload> <raw page csv made with: ncu -i X.ncu-rep --page raw --csv>"""
 import csv
 import hashlib
@@ -22,11 +22,13 @@ for vals in rows[2:]:                                     # the rollout_kernel l
     if best is None or dur > best[0]:
         tr = sum(float(d[k][1]) * UNIT[d[k][0]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         best = (dur, tr, d["gpu__time_duration.sum"][0])
-sha = hashlib.sha256(open(os.path.join(ROOT, "synthesize_pregrasp_b200", "libpregrasp_b200.so"), "rb").read()).hexdigest()[:16]
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+sha = bench._src_sha16()
 out_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 out = json.load(open(out_path)) if os.path.exists(out_path) else {}
-if out.get("lib_sha16") != sha:
-    out = {"lib_sha16": sha, "traffic_bytes": {}, "duration": {}}
+if out.get("src_sha16") != sha:
+    out = {"src_sha16": sha, "traffic_bytes": {}, "duration": {}}
 out["traffic_bytes"][workload] = best[1]
 out["duration"][workload] = f"{best[0]} {best[2]}"
 json.dump(out, open(out_path, "w"), indent=1)
