@@ -187,6 +187,9 @@ struct Params {
                                   // every other recording is indifferent
   double default_max_impulse = 500.0;
   int pair_flip = 0;              // debugging: reverse the uid rule for non-compound pairs
+  double fric_scale = 1.0;        // debugging: scales the floor friction at step dbg_step
+  double pos_drop = 0;            // debugging: at step dbg_step, drop cached points farther apart than this
+  int cone_variant = 0;           // debugging: alternative friction-cone clips
   int pos_variant = 0;            // debugging: alternative right-hand sides for contacts with positive distance
   int dbg_skip_new = 0;           // debugging: no new compound-child manifold at this step
   int dbg_step = 0, dbg_idx = -1; // debugging: force the cache slot of contacts added at one step
@@ -202,6 +205,7 @@ struct SolverRow {
   double dA[6], dB[6];      // unit-impulse velocity responses
   double rhs = 0, cfm = 0, lo = 0, hi = 0, inv = 0, imp = 0, friction = 0;
   int fric_of = -1;         // normal-row index for friction rows
+  double prev_imp = 0;      // debugging what-if: impulse before this iteration's update
   ManifoldPoint* cp = nullptr;
 };
 
@@ -357,10 +361,12 @@ static void refresh_manifold(World& w, Manifold& m) {
     ManifoldPoint& p = m.p[i];
     bool remove = false;
     if (!(p.dist <= m.breaking)) remove = true;
+    else if (w.P.pos_drop > 0 && w.step_count == w.P.dbg_step && p.dist > w.P.pos_drop) remove = true;      // debugging what-if
     else {
       V3 proj = p.posA - p.normalB * p.dist;
       V3 d = p.posB - proj;
       if (dot(d, d) > m.breaking * m.breaking) remove = true;
+      if (w.P.debug == 5) fprintf(stderr, "step %d refresh %d-%d slot %d dist %+.4e drift %.4e breaking %.4e life %d%s\n", w.step_count, m.a, m.b, i, p.dist, std::sqrt(dot(d, d)), m.breaking, p.life, remove ? " REMOVED" : "");
     }
     if (remove) {
       int last = m.n - 1;
@@ -459,6 +465,7 @@ static void cull_points2(int n, double p[], int m, int i0, int iret[]) {
 }
 
 static int g_last_code = 0, g_last_cnum = 0;
+static int g_bb_edge_point = 0;
 static double g_bb_fudge = 1.05;   // debugging: dBoxBox2's edge-axis preference factor
 static const bool g_bb_debug = getenv("PGO_BB_DEBUG") != nullptr;   // debugging: print every separating-axis value
 static int box_box(V3 p1, const M3& R1, V3 half1, V3 p2, const M3& R2, V3 half2, ContactSink& out) {
@@ -527,7 +534,9 @@ static int box_box(V3 p1, const M3& R1, V3 half1, V3 p2, const M3& R2, V3 half2,
     line_closest_approach(pa, ua, pb, ub, &alpha, &beta);
     pa += ua * alpha;
     pb += ub * beta;
-    add_contact(out, -normal, pb, -depth);
+    if (g_bb_edge_point == 1) add_contact(out, -normal, (pa + pb) * 0.5, -depth);     // debugging what-ifs (USE_CENTER_POINT)
+    else if (g_bb_edge_point == 2) add_contact(out, -normal, pa, -depth);
+    else add_contact(out, -normal, pb, -depth);
     return 1;
   }
 
@@ -580,6 +589,7 @@ static int box_box(V3 p1, const M3& R1, V3 half1, V3 p2, const M3& R2, V3 half2,
     V3 pt = center + Rb->col(a1) * k1 + Rb->col(a2) * k2;
     point[cnum * 3] = pt.x; point[cnum * 3 + 1] = pt.y; point[cnum * 3 + 2] = pt.z;
     dep[cnum] = Sa[codeN] - dot(normal2, pt);
+    if (g_bb_debug) fprintf(stderr, "    bb poly vertex %d/%d ret %.9f %.9f dep %.6e\n", j, n, ret[j * 2], ret[j * 2 + 1], dep[cnum]);
     if (dep[cnum] >= 0) { ret[cnum * 2] = ret[j * 2]; ret[cnum * 2 + 1] = ret[j * 2 + 1]; cnum++; }
   }
   if (cnum < 1) return 0;
@@ -851,6 +861,7 @@ static void setup_contact_row(World& w, SolverRow& r, const Manifold& m, Manifol
   rel_vel += body_vel_dot(A, r.jA);   // static bodies have zero velocity
   rel_vel += body_vel_dot(B, r.jB);
   r.friction = cp.friction;
+  if (P.fric_scale != 1.0 && w.step_count == P.dbg_step && A.compound) r.friction *= P.fric_scale;   // debugging what-if
   double distance = is_friction ? 0.0 : cp.dist + P.linear_slop;
   double positionalError = 0, velocityError = 0 - rel_vel;
   double erp = P.erp2;
@@ -899,6 +910,11 @@ static double resolve_row(World& w, SolverRow& r) {
 static double resolve_cone(World& w, SolverRow& cA, SolverRow& cB) {
   double dB = row_delta(w, cB), sumB = cB.imp + dB;
   double dA = row_delta(w, cA), sumA = cA.imp + dA;
+  const int cv = w.P.cone_variant;             // debugging what-ifs of the clip
+  if (cv == 1) {                               // per-axis box clip, Jacobi inside the pair
+    if (sumA < cA.lo) { dA = cA.lo - cA.imp; cA.imp = cA.lo; } else if (sumA > cA.hi) { dA = cA.hi - cA.imp; cA.imp = cA.hi; } else cA.imp = sumA;
+    if (sumB < cB.lo) { dB = cB.lo - cB.imp; cB.imp = cB.lo; } else if (sumB > cB.hi) { dB = cB.hi - cB.imp; cB.imp = cB.hi; } else cB.imp = sumB;
+  } else
   if (sumA * sumA + sumB * sumB >= cA.lo * cB.lo) {
     double angle = std::atan2(sumA, sumB);
     double sumAclipped = std::fabs(cA.lo * std::sin(angle));
@@ -1074,15 +1090,16 @@ static void solve(World& w) {
         acc(rr);
       }
       row_kind = 1;
-      for (auto& r : normal) { double rr = resolve_row(w, r); if (P.debug > 1 && w.step_count == 3) fprintf(stderr, "  normal bA %d bB %d res %.3e imp %.6e rhs %.3e\n", r.bA, r.bB, rr, r.imp, r.rhs); acc(rr); }
+      for (auto& r : normal) { r.prev_imp = r.imp; double rr = resolve_row(w, r); if (P.debug > 1 && w.step_count == 3) fprintf(stderr, "  normal bA %d bB %d res %.3e imp %.6e rhs %.3e\n", r.bA, r.bB, rr, r.imp, r.rhs); acc(rr); }
       row_kind = 2;
       if (P.two_dirs && P.cone_friction) {
         for (size_t j = 0; j + 1 < fric.size(); j += 2) {
           SolverRow& fa = fric[j];
           SolverRow& fb = fric[j + 1];
-          double total = normal[fa.fric_of].imp;
+          double total = P.cone_variant == 2 ? normal[fa.fric_of].prev_imp : normal[fa.fric_of].imp;
           fa.lo = -(fa.friction * total); fa.hi = fa.friction * total;
           fb.lo = -(fb.friction * total); fb.hi = fb.friction * total;
+          if (P.cone_variant == 3 && !(total > 0)) continue;      // debugging what-if: no friction update while the normal impulse is zero
           acc(resolve_cone(w, fa, fb));
         }
       } else {
@@ -1091,11 +1108,28 @@ static void solve(World& w) {
           if (total > 0) { f.lo = -(f.friction * total); f.hi = f.friction * total; acc(resolve_row(w, f)); }
         }
       }
+      if (P.debug == 6 && w.step_count >= P.dbg_step && w.step_count <= P.dbg_step + 1) {
+        fprintf(stderr, "step %d it %2d:", w.step_count, it);
+        for (size_t k = 0; k < normal.size(); k++) { double f1 = fric[2 * k].imp, f2 = fric[2 * k + 1].imp, lim = normal[k].friction * normal[k].imp;
+          fprintf(stderr, " [N %.5e r %.6f]", normal[k].imp, lim > 0 ? std::sqrt(f1 * f1 + f2 * f2) / lim : 0.0); }
+        fprintf(stderr, " servo");
+        for (size_t k = 0; k < nc.size(); k++) fprintf(stderr, " %+.3e", nc[k].imp);
+        fprintf(stderr, "\n");
+      }
       if (P.debug) fprintf(stderr, "step %d isl %d it %d residual^2 nc %.3e normal %.3e fric %.3e\n", w.step_count, isl, it, kind_max[0], kind_max[1], kind_max[2]);
       if (P.force_iters > 0 && w.step_count == P.force_step) { if (it + 1 >= P.force_iters) { it++; break; } else continue; }
       if (lsr <= P.residual_threshold || it >= P.iterations - 1) { it++; break; }
     }
     w.last_iterations = std::max(w.last_iterations, it);
+    if (P.debug == 4 && w.step_count >= P.dbg_step && w.step_count <= P.dbg_step + 2) {      // debugging: the solved impulses of one step
+      for (size_t k = 0; k < normal.size(); k++) {
+        const SolverRow& r = normal[k];
+        double f1 = 2 * k < fric.size() ? fric[2 * k].imp : 0, f2 = 2 * k + 1 < fric.size() ? fric[2 * k + 1].imp : 0;
+        fprintf(stderr, "step %d isl %d contact %zu (%d-%d) dist %+.3e impN %.6e fric %+.6e %+.6e |f|/(mu N) %.4f mu %.2f\n", w.step_count, isl, k, r.bA, r.bB,
+                r.cp->dist, r.imp, f1, f2, r.imp > 0 ? std::sqrt(f1 * f1 + f2 * f2) / (r.friction * r.imp) : 0.0, r.friction);
+      }
+      for (size_t k = 0; k < nc.size(); k++) fprintf(stderr, "step %d servo row %zu imp %+.6e lim %.3e\n", w.step_count, k, nc[k].imp, nc[k].hi);
+    }
     // write back
     for (size_t k = 0; k < normal.size(); k++) {
       ManifoldPoint* cp = normal[k].cp;
@@ -1162,13 +1196,14 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }
   if (!strcmp(name, "hull_inertia_pad")) { g_hull_inertia_pad = v; return; }
   if (!strcmp(name, "pen_tie")) { g_pen_tie = v; return; }
   if (!strcmp(name, "bb_fudge")) { g_bb_fudge = v; return; }
+  if (!strcmp(name, "bb_edge_point")) { g_bb_edge_point = (int)v; return; }
   if (!strcmp(name, "epa_variant")) { epa2::g_epa_variant = (int)v; return; }
   fprintf(stderr, "pgo_set_param: unknown %s\n", name);
 }
