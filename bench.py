@@ -267,7 +267,80 @@ def bench_multi_env(args, rank, world, local):
         dist.destroy_process_group()
 
 
-OTHER_WORKLOADS = {"dyn_sweep_P256": bench_dyn_sweep, "dyn_sweep_P1024": bench_dyn_sweep, "multi_env": bench_multi_env}
+def bench_mppi_update(args, rank, world, local):
+    """Row a2 alone: the exp-weighted update (stoch_traj_opt.py:195-204) over K = 2^20 samples per GPU -- the one kernel of the path
+    that is bound by HBM (it streams the noise once): min J, exp weights, sum of w * noise[K,N,D], update of u.  Every rank runs its
+    own K (the multi-GPU merge is 99 doubles per rank and is part of the rollout workloads)."""
+    import torch
+    import torch.distributed as dist
+    from synthesize_pregrasp_b200 import _abi
+    from synthesize_pregrasp_b200 import engine as EN
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K = args.K or (1 << 20)
+    dev = torch.device("cuda", local)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    noise = SIGMA * torch.randn((K, N_STEPS, D), generator=gen, device=dev, dtype=torch.float32)      # 403 MB > 126 MB L2
+    J = 1000.0 + 10.0 * torch.rand((K,), generator=gen, device=dev, dtype=torch.float64)
+    u = torch.zeros((N_STEPS, D), dtype=torch.float64, device=dev)
+    L = _abi.lib()
+    for _ in range(max(3, args.warmup)):
+        EN.mppi_update(J, noise, u, KAPPA, ALPHA)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local); sampler.start()
+    steps = max(args.steps, 5000)                       # ~0.1 ms each: long enough for the clock sampler to see the load
+    l0 = L.pg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        EN.mppi_update(J, noise, u, KAPPA, ALPHA)
+    e1.record(); torch.cuda.synchronize()
+    launches = int(L.pg_launch_count() - l0)
+    sampler.stop_flag = True; sampler.join()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier(); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    # end to end: host J and pinned host noise in, updated u out
+    noise_h = noise.cpu().pin_memory(); J_h = J.cpu().pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        nd = noise_h.to(dev, non_blocking=True); Jd = J_h.to(dev, non_blocking=True)
+        EN.mppi_update(Jd, nd, u, KAPPA, ALPHA); u_h = u.cpu()
+    e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
+    if rank == 0:
+        from oracle import mppi as OM
+        ks = 1 << 16
+        Jn, nn = J[:ks].cpu().numpy(), noise[:ks].cpu().numpy()
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < 3.0:
+            OM.mppi_update(np.zeros((N_STEPS, D)), Jn, nn, KAPPA, ALPHA); reps += 1
+        cpu = reps * ks / (time.perf_counter() - t0)
+        peaks = _peaks()
+        bytes_alg = K * (N_STEPS * D * 4 + 2 * 8)               # the noise once, J twice (min pass, weight pass)
+        ach = bytes_alg / (ms * 1e-3) / 1e9
+        print(json.dumps({"metric": "mppi-update samples/sec", "value": K * world / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": steps,
+                          "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64 accumulation over f32 noise", "data": "synthetic",
+                          "config": {"workload": args.workload, "K_per_gpu": K, "N": N_STEPS, "D": D, "kappa": KAPPA,
+                                     "l2": f"noise {K * N_STEPS * D * 4 / 1e6:.0f} MB > 126 MB L2"},
+                          "roofline": {"kernel": "mppi_min + mppi_accum<float4> + mppi_final", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"],
+                                       "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
+                                       "note": "algorithmic bytes = 4*N*D per sample (noise, read once) + 16 (J read by the min pass and the weight pass)"},
+                          "cpu_baseline": {"value": cpu, "unit": "samples/s", "cores": 1, "kind": "port",
+                                           "sample": f"{ks} samples through oracle/mppi.mppi_update (numpy: the reference's own lines) for 3 s"},
+                          "e2e": {"value": K * world / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": int(noise_h.nbytes + J_h.nbytes),
+                                  "d2h_bytes_per_step": int(u_h.numel() * 8)},
+                          "gpu_launches": launches, "clocks": sampler.summary(),
+                          "host_cores": os.cpu_count() or 1}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+OTHER_WORKLOADS = {"mppi_update_K1048576": bench_mppi_update, "dyn_sweep_P256": bench_dyn_sweep, "dyn_sweep_P1024": bench_dyn_sweep, "multi_env": bench_multi_env}
 
 
 def _lib_sha16():

@@ -18,3 +18,4 @@ tail -2 gpurun_out/${T}_plain2.log gpurun_out/${T}_ncu2.log
 python tools/gpu_cost_time.py bookshelf 16384 1 > gpurun_out/${T}_plain3.log 2>&1 &&
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:pcn_tc_kernel -s 1 -c 1 -o gpurun_out/${T}_cost python tools/gpu_cost_time.py bookshelf 16384 1 > gpurun_out/${T}_ncu3.log 2>&1
 tail -2 gpurun_out/${T}_ncu3.log; ls -la gpurun_out | tail -8
+timeout 300 python bench.py --workload mppi_update_K1048576 > gpurun_out/${T}_bench_mppi_update.json 2> gpurun_out/${T}_bench_mppi_update.err; cut -c1-400 gpurun_out/${T}_bench_mppi_update.json
