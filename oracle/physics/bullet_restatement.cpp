@@ -189,6 +189,8 @@ struct Params {
   int pair_flip = 0;              // debugging: reverse the uid rule for non-compound pairs
   double fric_scale = 1.0;        // debugging: scales the floor friction at step dbg_step
   double pos_drop = 0;            // debugging: at step dbg_step, drop cached points farther apart than this
+  int tip_skip_n = 0;             // ... and for this many further steps
+  int tip_skip = 0;               // debugging: no narrowphase for fingertip pairs at this step
   int cone_variant = 0;           // debugging: alternative friction-cone clips
   int pos_variant = 0;            // debugging: alternative right-hand sides for contacts with positive distance
   int dbg_skip_new = 0;           // debugging: no new compound-child manifold at this step
@@ -711,6 +713,7 @@ static void narrowphase(World& w, Manifold& m) {
   Body& A = w.bodies[m.a];
   Body& B = w.bodies[m.b];
   ContactSink sink{&w, &m, false};
+  if (w.P.tip_skip > 0 && w.step_count >= w.P.tip_skip && w.step_count <= w.P.tip_skip + w.P.tip_skip_n && (m.a == w.tip[0] || m.b == w.tip[0] || m.a == w.tip[1] || m.b == w.tip[1])) return;   // debugging what-if
   if (A.shape.type == SH_BOX && B.shape.type == SH_BOX) {
     int nbefore = m.n;
     box_box(A.pos, A.R, A.shape.half, B.pos, B.R, B.shape.half, sink);
@@ -1196,7 +1199,7 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }
