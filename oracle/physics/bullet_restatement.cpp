@@ -189,6 +189,8 @@ struct Params {
   int pair_flip = 0;              // debugging: reverse the uid rule for non-compound pairs
   double fric_scale = 1.0;        // debugging: scales the floor friction at step dbg_step
   double pos_drop = 0;            // debugging: at step dbg_step, drop cached points farther apart than this
+  int skip_body = -1, skip_other = -1;   // debugging: at step dbg_step the pair (skip_body, skip_other) is refreshed but not re-detected
+  int fs_idx0 = -1, fs_idx1 = -1; double fs_val0 = 1, fs_val1 = 1;
   int tip_skip_n = 0;             // ... and for this many further steps
   int tip_skip = 0;               // debugging: no narrowphase for fingertip pairs at this step
   int cone_variant = 0;           // debugging: alternative friction-cone clips
@@ -714,6 +716,8 @@ static void narrowphase(World& w, Manifold& m) {
   Body& B = w.bodies[m.b];
   ContactSink sink{&w, &m, false};
   if (w.P.tip_skip > 0 && w.step_count >= w.P.tip_skip && w.step_count <= w.P.tip_skip + w.P.tip_skip_n && (m.a == w.tip[0] || m.b == w.tip[0] || m.a == w.tip[1] || m.b == w.tip[1])) return;   // debugging what-if
+  const bool dbg_no_detect = w.P.skip_body >= 0 && w.step_count == w.P.dbg_step && (m.a == w.P.skip_body || m.b == w.P.skip_body) && (w.P.skip_other < 0 || m.a == w.P.skip_other || m.b == w.P.skip_other);   // debugging what-if: refresh only
+  if (dbg_no_detect) { refresh_manifold(w, m); return; }
   if (A.shape.type == SH_BOX && B.shape.type == SH_BOX) {
     int nbefore = m.n;
     box_box(A.pos, A.R, A.shape.half, B.pos, B.R, B.shape.half, sink);
@@ -1100,6 +1104,8 @@ static void solve(World& w) {
           SolverRow& fa = fric[j];
           SolverRow& fb = fric[j + 1];
           double total = P.cone_variant == 2 ? normal[fa.fric_of].prev_imp : normal[fa.fric_of].imp;
+          if (w.step_count == P.dbg_step && fa.fric_of == P.fs_idx0) total *= P.fs_val0;       // debugging what-ifs: per-contact scale of the cone
+          if (w.step_count == P.dbg_step && fa.fric_of == P.fs_idx1) total *= P.fs_val1;
           fa.lo = -(fa.friction * total); fa.hi = fa.friction * total;
           fb.lo = -(fb.friction * total); fb.hi = fb.friction * total;
           if (P.cone_variant == 3 && !(total > 0)) continue;      // debugging what-if: no friction update while the normal impulse is zero
@@ -1199,7 +1205,7 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }
