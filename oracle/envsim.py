@@ -31,6 +31,7 @@ def lib():
         L.pgo_add_body.argtypes = [ctypes.c_void_p, ctypes.c_int, dp, dp, ctypes.c_int, ctypes.c_double, dp, dp,
                                    ctypes.c_double, ctypes.c_int, ctypes.c_double]
         L.pgo_set_roles.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3
+        L.pgo_add_idle.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.pgo_set_filter.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 3
         L.pgo_reset_pose.argtypes = [ctypes.c_void_p, ctypes.c_int, dp, dp]
         L.pgo_get_pose.argtypes = [ctypes.c_void_p, ctypes.c_int, dp]
@@ -159,7 +160,7 @@ class EnvSim:
         self.close()
         self.h = self.L.pgo_create()
         for k, v in self.params.items():
-            if k == "obj_compound":
+            if k in ("obj_compound", "idle_tips"):
                 continue
             self.L.pgo_set_param(self.h, k.encode(), float(v))
         self.static_ids = {}
@@ -181,6 +182,17 @@ class EnvSim:
             t = self._add(0, half, None, 0.01, (f + 2.0,) * 3, (0, 0, 0, 1), s["tip_friction"])
             self.tips.append(t)
             self.L.pgo_set_filter(self.h, t, self.floor, 0)
+        # the env's inactive fingertips (plate_env:215-228: `all_fingers` = 0..4, only `active_finger_tips` = [0, 1] are ever
+        # moved): fingers 2-4 are created at the SAME place (100, 100, 100), so they collide with each other, are pushed apart and
+        # fall freely.  They never touch anything else, but their manifolds sit in the dispatcher's array and take part in the
+        # unstable quickSort by island id that fixes the solver's manifold order -- until they have drifted apart (world steps 20
+        # and 39), after which the order of everybody else's manifolds flips (keyboard_20.0 row 37).
+        self.idle = []
+        for f in range(2, 2 + int(self.params.get("idle_tips", 3))):
+            t = self._add(0, s["tip_half"][1], None, 0.01, (100.0, 100.0, 100.0), (0, 0, 0, 1), s["tip_friction"])
+            self.idle.append(t)
+            self.L.pgo_set_filter(self.h, t, self.floor, 0)
+            self.L.pgo_add_idle(self.h, t)
         self.L.pgo_set_roles(self.h, self.obj, self.tips[0], self.tips[1])
         self.carry = D.new_carry()
         self.L.pgo_step(self.h)                              # :237

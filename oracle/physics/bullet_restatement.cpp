@@ -190,6 +190,9 @@ struct Params {
   double fric_scale = 1.0;        // debugging: scales the floor friction at step dbg_step
   double pos_drop = 0;            // debugging: at step dbg_step, drop cached points farther apart than this
   int skip_body = -1, skip_other = -1;   // debugging: at step dbg_step the pair (skip_body, skip_other) is refreshed but not re-detected
+  int marginal_rule = 1;          // the round-1 fitted rule for a merely touching fingertip (see refresh_proxy)
+  int idle_order = 0;             // creation order of the idle fingertips' pairs: 0: (2,3),(2,4),(3,4); 1: (2,3),(3,4),(2,4)
+  int find_order = 12345;         // order in which the re-created object proxy finds its pairs: digits 1 first wall, 2 index tip (early), 3 thumb (early), 4 compound floor, 5 other walls
   int fs_idx0 = -1, fs_idx1 = -1; double fs_val0 = 1, fs_val1 = 1;
   int tip_skip_n = 0;             // ... and for this many further steps
   int tip_skip = 0;               // debugging: no narrowphase for fingertip pairs at this step
@@ -221,6 +224,7 @@ struct World {
   FixedConstraint cons[2];
   long next_uid = 1;
   int obj = -1, tip[2] = {-1, -1}, floor_body = -1;
+  std::vector<int> idle;        // the env's inactive fingertips (plate_env:215-228: fingers 2-4, all created at (100,100,100))
   int last_iterations = 0;
   int step_count = 0;
   // scratch
@@ -469,7 +473,7 @@ static void cull_points2(int n, double p[], int m, int i0, int iret[]) {
 }
 
 static int g_last_code = 0, g_last_cnum = 0;
-static int g_bb_edge_point = 0;
+static int g_bb_edge_point = 0, g_bb_edge_flip = 0;
 static double g_bb_fudge = 1.05;   // debugging: dBoxBox2's edge-axis preference factor
 static const bool g_bb_debug = getenv("PGO_BB_DEBUG") != nullptr;   // debugging: print every separating-axis value
 static int box_box(V3 p1, const M3& R1, V3 half1, V3 p2, const M3& R2, V3 half2, ContactSink& out) {
@@ -526,11 +530,13 @@ static int box_box(V3 p1, const M3& R1, V3 half1, V3 p2, const M3& R2, V3 half2,
     V3 pa = p1;
     for (j = 0; j < 3; j++) {
       double sign = (dot(normal, R1.col(j)) > 0) ? 1.0 : -1.0;
+      if ((g_bb_edge_flip >> j) & 1) sign = -sign;           // debugging what-if
       pa += R1.col(j) * (sign * A[j]);
     }
     V3 pb = p2;
     for (j = 0; j < 3; j++) {
       double sign = (dot(normal, R2.col(j)) > 0) ? -1.0 : 1.0;
+      if ((g_bb_edge_flip >> (3 + j)) & 1) sign = -sign;     // debugging what-if
       pb += R2.col(j) * (sign * B[j]);
     }
     double alpha, beta;
@@ -692,7 +698,7 @@ static void refresh_proxy(World& w, int body) {
       // [H] a tip that merely touches the object (overlap below 1e-6: placed exactly on a face) is found at creation
       // only when it is the single active tip; with the other tip clearly overlapping it enters the cache later
       bool marginal = depth[t] < 1e-6, other_clear = depth[1 - t] >= 1e-6;
-      w.bodies[w.tip[t]].early = depth[t] >= 0 && !(marginal && other_clear);
+      w.bodies[w.tip[t]].early = depth[t] >= 0 && !(marginal && other_clear && w.P.marginal_rule);
       if (w.P.debug == 1) fprintf(stderr, "refresh obj: tip %d overlap %.3g early %d\n", t, depth[t], (int)w.bodies[w.tip[t]].early);
     }
   }
@@ -754,6 +760,12 @@ static void collide(World& w) {
     // surviving tip-tip / wall-tip pairs, then what the re-created object proxy found at creation -- dynamic tree
     // first (index tip, thumb: only tips whose tight AABB overlapped), then the static tree -- then the tip pairs
     // the first updateAabbs finds with fat AABBs.  Tree traversal orders are fitted to the recorded trajectories.
+    // the idle fingertips overlap each other from the moment they are created: their pairs are the oldest of the cache
+    if (w.idle.size() == 3) {
+      push(w.idle[0], w.idle[1]);
+      if (w.P.idle_order == 0) { push(w.idle[0], w.idle[2]); push(w.idle[1], w.idle[2]); }
+      else { push(w.idle[1], w.idle[2]); push(w.idle[0], w.idle[2]); }
+    }
     bool tt_early = false;
     if (w.tip[0] >= 0 && w.tip[1] >= 0) {
       const Body& a = w.bodies[w.tip[0]]; const Body& b = w.bodies[w.tip[1]];
@@ -762,10 +774,21 @@ static void collide(World& w) {
     }
     if (tt_early) push(w.tip[0], w.tip[1]);
     for (int i = 0; i < nb; i++) if (w.bodies[i].is_static && !w.bodies[i].compound) { push(i, w.tip[1]); push(i, w.tip[0]); }
-    { int k = 0; for (int i = 0; i < nb && k < w.P.walls_first; i++) if (w.bodies[i].is_static && !w.bodies[i].compound) { push(w.obj, i); k++; } }
-    for (int t = 1; t >= 0; t--) if (w.tip[t] >= 0 && w.bodies[w.tip[t]].early) push(w.obj, w.tip[t]);
-    for (int i = 0; i < nb; i++) if (w.bodies[i].compound && i != w.obj) push(w.obj, i);
-    for (int i = 0; i < nb; i++) if (w.bodies[i].is_static && !w.bodies[i].compound) push(w.obj, i);
+    {
+      int digits[8], nd = 0;
+      for (int c = w.P.find_order; c > 0; c /= 10) digits[nd++] = c % 10;
+      for (int q = nd - 1; q >= 0; q--) {
+        switch (digits[q]) {
+          case 1: { int k = 0; for (int i = 0; i < nb && k < w.P.walls_first; i++) if (w.bodies[i].is_static && !w.bodies[i].compound) { push(w.obj, i); k++; } } break;
+          case 2: if (w.tip[1] >= 0 && w.bodies[w.tip[1]].early) push(w.obj, w.tip[1]); break;
+          case 3: if (w.tip[0] >= 0 && w.bodies[w.tip[0]].early) push(w.obj, w.tip[0]); break;
+          case 4: for (int i = 0; i < nb; i++) if (w.bodies[i].compound && i != w.obj) push(w.obj, i); break;
+          case 5: for (int i = 0; i < nb; i++) if (w.bodies[i].is_static && !w.bodies[i].compound) push(w.obj, i); break;
+          case 6: case 7: case 8: { int k = 0; for (int i = 0; i < nb; i++) if (w.bodies[i].is_static && !w.bodies[i].compound) { if (k == digits[q] - 6) push(w.obj, i); k++; } } break;   // wall #0, #1, #2 on its own
+          case 9: for (int i = nb - 1; i >= 0; i--) if (w.bodies[i].is_static && !w.bodies[i].compound) push(w.obj, i); break;                                       // all walls, youngest first
+        }
+      }
+    }
     for (int t = 1; t >= 0; t--) if (w.tip[t] >= 0 && !w.bodies[w.tip[t]].early) push(w.obj, w.tip[t]);
   }
   for (int i = 0; i < nb; i++) for (int j = i + 1; j < nb; j++) {
@@ -1034,12 +1057,12 @@ static void solve(World& w) {
       std::sort(mlist.begin(), mlist.end());
       std::vector<int> src = mlist; int code = P.manifold_order3;
       for (int k = nd3 - 2; k >= 0; k--) { mlist[k] = src[code % 10]; code /= 10; }
-    } else if (P.manifold_order >= 10000 && mlist.size() > 1) {
+    } else if (P.manifold_order >= 10000 && mlist.size() > 1 && w.step_count >= P.order_step_min) {
       // explicit order: digits of (manifold_order - 10000), zero padded to mlist.size(), index creation order
       std::sort(mlist.begin(), mlist.end());
       std::vector<int> src = mlist; int code = P.manifold_order - 10000; int n = (int)src.size();
       for (int k = n - 1; k >= 0; k--) { int dgt = code % 10; code /= 10; if (dgt < n) mlist[k] = src[dgt]; }
-    } else if (P.manifold_order > 0 && mlist.size() > 1) {
+    } else if (P.manifold_order > 0 && P.manifold_order < 10000 && mlist.size() > 1) {
       std::sort(mlist.begin(), mlist.end());
       for (int k = 0; k < P.manifold_order - 1; k++) std::next_permutation(mlist.begin(), mlist.end());
     }
@@ -1205,7 +1228,7 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(idle_order) S(marginal_rule) S(find_order) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }
@@ -1213,6 +1236,7 @@ void pgo_set_param(void* h, const char* name, double v) {
   if (!strcmp(name, "pen_tie")) { g_pen_tie = v; return; }
   if (!strcmp(name, "bb_fudge")) { g_bb_fudge = v; return; }
   if (!strcmp(name, "bb_edge_point")) { g_bb_edge_point = (int)v; return; }
+  if (!strcmp(name, "bb_edge_flip")) { g_bb_edge_flip = (int)v; return; }
   if (!strcmp(name, "epa_variant")) { epa2::g_epa_variant = (int)v; return; }
   fprintf(stderr, "pgo_set_param: unknown %s\n", name);
 }
@@ -1278,6 +1302,8 @@ int pgo_add_body(void* h, int type, const double* half, const double* verts, int
 void pgo_set_roles(void* h, int obj, int tip0, int tip1) {
   World& w = *(World*)h; w.obj = obj; w.tip[0] = tip0; w.tip[1] = tip1;
 }
+
+void pgo_add_idle(void* h, int body) { ((World*)h)->idle.push_back(body); }
 
 void pgo_set_filter(void* h, int a, int b, int enable) { set_collision_filter(*(World*)h, a, b, enable != 0); }
 

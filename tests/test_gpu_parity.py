@@ -497,6 +497,30 @@ def test_two_env_handles_on_two_streams(EN):
         assert torch.equal(a, b)
 
 
+def test_two_devices_in_one_process(EN):
+    """pg_env_create(spec, device): engines on two GPUs of one process (per-device kernel attributes, per-handle scratch, the MPPI
+    update on the second device) give the same results bit for bit.  Needs two visible GPUs (skipped on a one-GPU box)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    from synthesize_pregrasp_b200.envspec import make_spec
+    outs = []
+    for dev in (1, 0):                                            # the second device first: nothing may rely on device 0's state
+        eng = EN.RolloutEngine(make_spec("plate"), device=dev)
+        gen = torch.Generator(device=f"cuda:{dev}").manual_seed(21)
+        noise = 0.8 * torch.randn((200, 2, 48), generator=gen, device=f"cuda:{dev}", dtype=torch.float32)
+        u = torch.zeros((2, 48), dtype=torch.float64, device=f"cuda:{dev}")
+        J = eng.rollout(u, noise, [0, 0], 20.0)
+        with torch.cuda.device(dev):
+            EN.mppi_update(J, noise, u, 5.0, 1.0)
+        torch.cuda.synchronize(dev)
+        outs.append((noise.cpu(), J.cpu(), u.cpu()))
+        Jh = eng.rollout_host(np.zeros((2, 48)), noise.cpu().numpy(), [0, 0], 20.0)
+        assert np.array_equal(Jh, J.cpu().numpy())
+        eng.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
 def test_csg_node_scores_match_oracle(EN):
     """generate_csg.node_scores: all (node x sample) score evaluations in one pg_score launch vs the oracle network."""
     from oracle import scorenet as SN
