@@ -190,9 +190,9 @@ struct Params {
   double fric_scale = 1.0;        // debugging: scales the floor friction at step dbg_step
   double pos_drop = 0;            // debugging: at step dbg_step, drop cached points farther apart than this
   int skip_body = -1, skip_other = -1;   // debugging: at step dbg_step the pair (skip_body, skip_other) is refreshed but not re-detected
-  int marginal_rule = 1;          // the round-1 fitted rule for a merely touching fingertip (see refresh_proxy)
+  int marginal_rule = 0;          // 1: the round-1 rule for a merely touching fingertip (fitted without the idle fingertips; obsolete)
   int idle_order = 0;             // creation order of the idle fingertips' pairs: 0: (2,3),(2,4),(3,4); 1: (2,3),(3,4),(2,4)
-  int find_order = 12345;         // order in which the re-created object proxy finds its pairs: digits 1 first wall, 2 index tip (early), 3 thumb (early), 4 compound floor, 5 other walls
+  int find_order = 4239;          // [H] order in which the re-created object proxy finds its pairs: digits 4 compound floor, 2 index tip, 3 thumb (tips whose tight AABB overlapped), 9 walls youngest first (1 / 5 / 6-8: round-1 and per-wall variants)
   int fs_idx0 = -1, fs_idx1 = -1; double fs_val0 = 1, fs_val1 = 1;
   int tip_skip_n = 0;             // ... and for this many further steps
   int tip_skip = 0;               // debugging: no narrowphase for fingertip pairs at this step

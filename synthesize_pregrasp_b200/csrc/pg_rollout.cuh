@@ -208,7 +208,9 @@ PG_HD void env_reset(const EnvDev& E, Sim& S, const M3* statR, RowSet& rs, Carry
       t.half = V3(E.tip_half[f][0], E.tip_half[f][1], E.tip_half[f][2]); t.friction = E.tip_friction;
     }
   }
-  S.nman = 0; S.filter_off = 0; S.obj_first = 1; S.last_iterations = 0; S.early = 0; S.sync_cta = sync_cta;
+  S.nman = 0; S.step = 0;
+  S.ndisp = 3; S.disp[0] = DISP_IDLE; S.disp[1] = DISP_IDLE + 1; S.disp[2] = DISP_IDLE + 2;     // the idle fingertips' pairs are the oldest (pg_physics.cuh)
+  S.filter_off = 0; S.obj_first = 1; S.last_iterations = 0; S.early = 0; S.sync_cta = sync_cta;
   for (int f = 0; f < 2; f++) { S.plo[f] = V3(); S.phi[f] = V3(); }
   S.cons[0].active = 0; S.cons[1].active = 0;
   substep<SHAPE>(E, S, statR, rs, sm, ss);                                                       // :237

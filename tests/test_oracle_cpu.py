@@ -125,13 +125,15 @@ def test_physics_oracle_against_recorded_trajectories(exp):
     # whole 100-substep horizon stays physically close (contact-rich motion is chaotic)
     assert err[:, :3].max() <= 5e-2
     if exp == "waterbottle_20.0":
-        assert err[:18].max() <= 1e-8
+        assert err[:33].max() <= 1.5e-8
     if exp == "keyboard_20.0":
-        assert err[:37].max() <= 1e-10
+        assert err[:24].max() <= 1e-12
+    if exp == "foodbox_20.0":
+        assert err[:13].max() <= 1e-12 and err[:18].max() <= 1.5e-8
     if exp == "plate_20.0":
         assert err[:7].max() <= 1e-10
     if exp == "cardboard_20.0":
-        assert err[:51].max() <= 1e-12 and err.max() <= 2e-3          # env step 1 exact; whole horizon within 1e-3
+        assert err[:70].max() <= 1e-12 and err.max() <= 1e-11          # the whole horizon at rounding level
 
 
 def test_physics_oracle_resting_contact_exact():
