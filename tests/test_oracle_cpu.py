@@ -136,6 +136,45 @@ def test_physics_oracle_against_recorded_trajectories(exp):
         assert err[:70].max() <= 1e-12 and err.max() <= 1e-11          # the whole horizon at rounding level
 
 
+def test_physics_oracle_parked_fingertip_meets_idle_ones():
+    """wall_laptop_20.0 parks its thumb at (100, 100, 100) in the first env step -- where the env's idle fingertips were created.  In
+    PyBullet they collide; the manifolds this creates and releases (world step 9) re-order the object's rows.  With that interaction
+    switched on the oracle follows the recording three rows further (7-9) at rounding level; it is off by default because the CUDA
+    kernel carries the idle fingertips only as entries of the dispatcher array."""
+    from oracle.envsim import EnvSim
+    g = recorded("wall_laptop_20.0")
+    sim = EnvSim(oracle_spec(make_spec(g["env"])), g["max_force"], params=dict(tip_idle_collide=1))
+    sim.reset()
+    P = np.concatenate([sim.step(g["u"][j], [0, 0, 0])["poses"] for j in range(2)])
+    err = np.minimum(np.abs(P - g["poses"]), np.abs(P * np.r_[1, 1, 1, -1, -1, -1, -1] - g["poses"]))
+    assert err[:10].max() <= 1e-12, err[:10].max(axis=1)
+
+
+def test_idle_fingertips_timeline():
+    """The three idle fingertips alone (every env creates them at the same point): their pairs' fat AABBs separate during world
+    steps 20 (outer pair) and 39 (both inner pairs) -- the constants the CUDA kernel uses (pg_physics.cuh idle_pair_alive) -- for
+    every fingertip size and friction the envs use."""
+    import ctypes
+    from oracle import envsim as OE
+    L = OE.lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    for hz, fr in ((0.01, 5.0), (0.011, 100.0), (0.012, 100.0), (0.011, 150.0)):
+        h = L.pgo_create()
+        keep = []
+        for f in range(3):
+            arrs = [np.array([0.01, 0.01, hz]), np.zeros((0, 3)), np.array([100.0, 100.0, 100.0]), np.array([0, 0, 0, 1.0])]
+            keep.append(arrs)
+            L.pgo_add_body(h, 0, arrs[0].ctypes.data_as(dp), arrs[1].ctypes.data_as(dp), 0, 0.01, arrs[2].ctypes.data_as(dp),
+                           arrs[3].ctypes.data_as(dp), fr, 0, 0.001)
+        L.pgo_set_roles(h, -1, -1, -1)
+        counts = []
+        for s in range(1, 45):
+            L.pgo_step(h)
+            counts.append(L.pgo_num_manifolds(h))
+        L.pgo_destroy(h)
+        assert counts[:19] == [3] * 19 and counts[19:38] == [2] * 19 and counts[38:] == [0] * 6, counts
+
+
 def test_physics_oracle_resting_contact_exact():
     """keyboard_scale_20.0 was recorded with another region table: its thumb hovers 1.2e-8 above the top face for the whole first
     env step (ours, decoded by the committed env, overlaps by 1.1e-8), so PyBullet has no fingertip contact there.  With the
