@@ -499,9 +499,8 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
   // (every call re-creates both proxies) the cache holds: the surviving tip-tip and wall-tip pairs, then what the
   // re-created object proxy found at creation, then the tip pairs found with fat AABBs (DESIGN.md "Row order").
   int ca[MAXM + 6], cb[MAXM + 6], nc = 0;
-  bool tt_early = true;
-  for (int k = 0; k < 3; k++) if (S.plo[0][k] > S.phi[1][k] || S.phi[0][k] < S.plo[1][k]) tt_early = false;
-  if (tt_early) { ca[nc] = B_TIP0; cb[nc++] = B_TIP1; }
+  // (the fingertip-fingertip pair comes after the object's pairs even when the two tight proxies overlapped -- two parked
+  // fingertips, or both on the same rim: plate_20.0, start of env step 2)
   for (int s = 0; s < E.n_static; s++) if (!E.statics[s].compound) { ca[nc] = s; cb[nc++] = B_TIP1; ca[nc] = s; cb[nc++] = B_TIP0; }
   // what the re-created object proxy finds at creation: the floor, the fingertips whose tight AABB overlaps (index, thumb), the
   // walls youngest first (fitted to the seven recordings with the idle fingertips in the dispatcher's array; round 1, without
@@ -510,7 +509,7 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
   for (int t = 1; t >= 0; t--) if ((S.early >> t) & 1u) { ca[nc] = B_OBJ; cb[nc++] = B_TIP0 + t; }
   for (int s = E.n_static - 1; s >= 0; s--) if (!E.statics[s].compound) { ca[nc] = s; cb[nc++] = B_OBJ; }
   for (int t = 1; t >= 0; t--) if (!((S.early >> t) & 1u)) { ca[nc] = B_OBJ; cb[nc++] = B_TIP0 + t; }
-  if (!tt_early) { ca[nc] = B_TIP0; cb[nc++] = B_TIP1; }
+  ca[nc] = B_TIP0; cb[nc++] = B_TIP1;
   for (int c = 0; c < nc; c++) {
     int i = ca[c] < cb[c] ? ca[c] : cb[c], j = ca[c] < cb[c] ? cb[c] : ca[c];
     if (!pair_allowed(E, S, i, j)) continue;

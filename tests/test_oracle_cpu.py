@@ -132,6 +132,7 @@ def test_physics_oracle_against_recorded_trajectories(exp):
         assert err[:13].max() <= 1e-12 and err[:18].max() <= 1.5e-8
     if exp == "plate_20.0":
         assert err[:7].max() <= 1e-10
+        assert err[:53].max() <= 1e-6          # two substeps into env step 2 (fingertip-fingertip pair after the object's pairs)
     if exp == "cardboard_20.0":
         assert err[:70].max() <= 1e-12 and err.max() <= 1e-11          # the whole horizon at rounding level
 
