@@ -191,6 +191,7 @@ struct Params {
   double pos_drop = 0;            // debugging: at step dbg_step, drop cached points farther apart than this
   int skip_body = -1, skip_other = -1;   // debugging: at step dbg_step the pair (skip_body, skip_other) is refreshed but not re-detected
   int marginal_rule = 0;          // 1: the round-1 rule for a merely touching fingertip (fitted without the idle fingertips; obsolete)
+  int compound_prerefresh = 1;    // see narrowphase()
   int tt_never_early = 1;         // [H] the fingertip-fingertip pair enters the cache after the object's pairs (plate_20.0, start of env step 2: row 51 6e-5 -> 4e-7); 0: round-1 rule (first when the tight proxies overlapped)
   int tip_idle_collide = 0;       // see collide(): parked active fingertips vs idle ones
   int tip_idle_order = 0;         // order of a parked fingertip's pairs with the idle ones: 0 ascending, 1 descending, -1: found last (generic)
@@ -342,9 +343,12 @@ static void add_contact(ContactSink& s, V3 normalOnB, V3 pointOnB, double depth)
   np.friction = f;
   plane_space1(np.normalB, np.lat1, np.lat2);
   int idx = manifold_cache_entry(m, np);
-  if (s.w->P.dbg_step > 0 && s.w->step_count == s.w->P.dbg_step && m.n == 4 &&
+  if (s.w->P.dbg_step > 0 && s.w->step_count == s.w->P.dbg_step && (m.n == 4 || s.w->P.dbg_idx >= 10) &&
       (m.a == s.w->tip[0] || m.a == s.w->tip[1] || m.b == s.w->tip[0] || m.b == s.w->tip[1])) {     // debugging: what-if on one insertion
     if (s.w->P.dbg_idx == 9) return;
+    if (s.w->P.dbg_idx == 10) idx = -1;                       // add as a new point instead of replacing
+    if (s.w->P.dbg_idx >= 11 && s.w->P.dbg_idx <= 14) idx = s.w->P.dbg_idx - 11 < m.n ? s.w->P.dbg_idx - 11 : idx;   // replace this slot
+    if (s.w->P.dbg_idx == 19) return;                         // drop the point
     if (s.w->P.dbg_idx >= 0) { if (s.w->P.debug) fprintf(stderr, "dbg: natural idx %d -> %d\n", idx, s.w->P.dbg_idx); idx = s.w->P.dbg_idx; }
   }
   if (idx >= 0) {
@@ -727,6 +731,10 @@ static void narrowphase(World& w, Manifold& m) {
   if (w.P.tip_skip > 0 && w.step_count >= w.P.tip_skip && w.step_count <= w.P.tip_skip + w.P.tip_skip_n && (m.a == w.tip[0] || m.b == w.tip[0] || m.a == w.tip[1] || m.b == w.tip[1])) return;   // debugging what-if
   const bool dbg_no_detect = w.P.skip_body >= 0 && w.step_count == w.P.dbg_step && (m.a == w.P.skip_body || m.b == w.P.skip_body) && (w.P.skip_other < 0 || m.a == w.P.skip_other || m.b == w.P.skip_other);   // debugging what-if: refresh only
   if (dbg_no_detect) { refresh_manifold(w, m); return; }
+  // btCompoundCollisionAlgorithm::processCollision refreshes the contact points of its child manifolds BEFORE it runs the child
+  // algorithm (which refreshes them again afterwards): cached points that have drifted away are gone before the new ones arrive,
+  // and a new point that has to displace one of four cached points (sortCachedPoints) is compared with their CURRENT depths
+  if ((A.compound || B.compound) && w.P.compound_prerefresh) refresh_manifold(w, m);
   if (A.shape.type == SH_BOX && B.shape.type == SH_BOX) {
     int nbefore = m.n;
     box_box(A.pos, A.R, A.shape.half, B.pos, B.R, B.shape.half, sink);
@@ -1245,7 +1253,7 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(idle_order) S(tip_idle_order) S(tip_idle_collide) S(tt_never_early) S(marginal_rule) S(find_order) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(idle_order) S(tip_idle_order) S(tip_idle_collide) S(tt_never_early) S(compound_prerefresh) S(marginal_rule) S(find_order) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }

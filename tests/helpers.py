@@ -59,8 +59,8 @@ def oracle_weights():
 PHYS = {  # exp: (rows to check, tolerance on pose) -- achieved tolerances, see DESIGN.md "Oracle / physics"
     # With pybullet.multiplyTransforms emulated in float32 (oracle/envsim.py b3_multiply_transforms) AND the env's three idle
     # fingertips in the world (their manifolds take part in the dispatcher's unstable sort until world steps 20 / 39) the agreement
-    # is at rounding level up to the first edge-edge box-box result (keyboard row 43, laptop row 7) or hull event
-    "foodbox_20.0": (range(0, 29), 5e-8), "keyboard_20.0": (range(0, 43), 1e-11), "keyboard_scale_20.0": (range(0, 50), 5e-7),
+    # is at rounding level over whole recordings (cardboard, keyboard: both env steps) or up to the first event not yet restated
+    "foodbox_20.0": (range(0, 29), 5e-8), "keyboard_20.0": (range(0, 100), 1e-11), "keyboard_scale_20.0": (range(0, 50), 5e-7),
     "wall_laptop_20.0": (range(0, 7), 1e-12),
     # the whole recording, both env steps (floor friction of recording time, RECORDING_TIME below)
     "cardboard_20.0": (range(0, 100), 1e-11),
