@@ -531,6 +531,15 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
     double ta = bs_radius(E, m.a) * E.breaking_factor, tb = bs_radius(E, m.b) * E.breaking_factor;
     m.breaking = ta < tb ? ta : tb;
   }
+  // btCompoundCollisionAlgorithm refreshes the contact points of its child manifolds BEFORE it runs the child algorithm (which
+  // refreshes them again afterwards): drifted points are gone before the new ones arrive, and a new point that has to displace
+  // one of four cached points is compared with their CURRENT depths (keyboard_20.0 row 43: the first time the floor's box-box
+  // result has five points; with this the whole recording is reproduced).  A loop of its own: the same call placed inside the
+  // barrier-aligned loop below produced a wrong device build (host build fine) -- profiles/README.md, round 2.
+  for (int k = 0; k < S.nman; k++) {
+    Manifold& m = S.man[k];
+    if (m.n > 0 && (is_compound(m.a) || is_compound(m.b))) refresh(m, bv[m.a], bv[m.b]);
+  }
   for (int k = 0;; k++) {
     const bool live = k < S.nman;
 #if defined(__CUDA_ARCH__) && defined(PG_SUBSTEP_BARRIER)
@@ -541,11 +550,6 @@ PG_HDN void collide(const EnvDev& E, Sim& S, const M3* statR) {
     if (!live) break;
 #endif
     Manifold& m = S.man[k];
-    // btCompoundCollisionAlgorithm refreshes the contact points of its child manifolds BEFORE it runs the child algorithm (which
-    // refreshes them again afterwards): drifted points are gone before the new ones arrive, and a new point that has to displace
-    // one of four cached points is compared with their CURRENT depths (keyboard_20.0 row 43: the first time the floor's box-box
-    // result has five points; with this the whole recording is reproduced)
-    if (is_compound(m.a) || is_compound(m.b)) refresh(m, bv[m.a], bv[m.b]);
     Sink sink;
     sink.m = &m; sink.posA = bv[m.a].pos; sink.posB = bv[m.b].pos; sink.RA = bv[m.a].R; sink.RB = bv[m.b].R;
     if (SHAPE == SHAPE_HULL && (m.a == B_OBJ || m.b == B_OBJ)) {
