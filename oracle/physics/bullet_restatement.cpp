@@ -191,6 +191,7 @@ struct Params {
   double pos_drop = 0;            // debugging: at step dbg_step, drop cached points farther apart than this
   int skip_body = -1, skip_other = -1;   // debugging: at step dbg_step the pair (skip_body, skip_other) is refreshed but not re-detected
   int marginal_rule = 0;          // 1: the round-1 rule for a merely touching fingertip (fitted without the idle fingertips; obsolete)
+  int drop_scan_reverse = 0;      // see collide()
   int tipwall_order = 0;          // order of the (wall, fingertip) pairs, see collide()
   int compound_prerefresh = 1;    // see narrowphase()
   int tt_never_early = 1;         // [H] the fingertip-fingertip pair enters the cache after the object's pairs (plate_20.0, start of env step 2: row 51 6e-5 -> 4e-7); 0: round-1 rule (first when the tight proxies overlapped)
@@ -751,6 +752,12 @@ static void collide(World& w) {
   int nb = (int)w.bodies.size();
   if (w.P.debug == 7 && nb > 6) fprintf(stderr, "step %d aabb: body4 hi.x %.12e  body6 lo.x %.12e  gap %.3e\n", w.step_count, w.bodies[4].aabb_hi.x, w.bodies[6].aabb_lo.x, w.bodies[6].aabb_lo.x - w.bodies[4].aabb_hi.x);
   // drop pairs whose AABBs separated
+  if (w.P.drop_scan_reverse) {                 // debugging what-if: the broadphase's clean-up scan starts at a rotating index
+    for (int i = (int)w.manifolds.size() - 1; i >= 0; i--) {
+      Manifold& m = w.manifolds[i];
+      if (!pair_overlap(w, w.bodies[m.a], w.bodies[m.b])) { w.manifolds[i] = w.manifolds.back(); w.manifolds.pop_back(); }
+    }
+  } else
   for (size_t i = 0; i < w.manifolds.size();) {
     Manifold& m = w.manifolds[i];
     if (!pair_overlap(w, w.bodies[m.a], w.bodies[m.b])) { w.manifolds[i] = w.manifolds.back(); w.manifolds.pop_back(); }
@@ -1262,7 +1269,7 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(idle_order) S(tip_idle_order) S(tip_idle_collide) S(tt_never_early) S(compound_prerefresh) S(tipwall_order) S(marginal_rule) S(find_order) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(idle_order) S(tip_idle_order) S(tip_idle_collide) S(tt_never_early) S(compound_prerefresh) S(tipwall_order) S(drop_scan_reverse) S(marginal_rule) S(find_order) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }
