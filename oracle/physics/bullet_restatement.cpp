@@ -1275,6 +1275,9 @@ void pgo_set_param(void* h, const char* name, double v) {
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }
   if (!strcmp(name, "hull_inertia_pad")) { g_hull_inertia_pad = v; return; }
   if (!strcmp(name, "pen_tie")) { g_pen_tie = v; return; }
+  if (!strcmp(name, "gjk_rel_error2")) { g_gjk_rel_error2 = v; return; }
+  if (!strcmp(name, "gjk_pen_tol")) { g_gjk_pen_tol = v; return; }
+  if (!strcmp(name, "gjk_org_rule")) { g_gjk_org_rule = (int)v; return; }
   if (!strcmp(name, "bb_fudge")) { g_bb_fudge = v; return; }
   if (!strcmp(name, "bb_edge_point")) { g_bb_edge_point = (int)v; return; }
   if (!strcmp(name, "bb_edge_flip")) { g_bb_edge_flip = (int)v; return; }

@@ -593,12 +593,14 @@ PG_HDN bool pen_depth(const Shape& sA, const Xf& xA, const Shape& sB, const Xf& 
 // returns true and (normal on B in world, point on B in world, signed distance) when a point should be added
 PG_HDN bool closest_points(const Shape& sA, V3 posA, const M3& RA, const Shape& sB, V3 posB, const M3& RB, double breaking,
                            Scratch& sc, V3& normal_out, V3& point_b_out, double& dist_out) {
-  const double REL2 = 1.0e-6, EPS = 2.220446049250313e-16;
+  // REL_ERROR2 and gGjkEpaPenetrationTolerance of a BT_USE_DOUBLE_PRECISION build (btGjkPairDetector.cpp): 1e-12 both (the
+  // single-precision 1e-6 / 0.001 sent touching pairs with cores less than 1 mm apart to EPA; plate_20.0 says no)
+  const double REL2 = 1.0e-12, PEN_TOL = 1.0e-12, EPS = 2.220446049250313e-16;
   double mA = sA.margin, mB = sB.margin, margin = mA + mB;
   double maxd = margin + breaking, max_dist2 = maxd * maxd;
   V3 offset = (posA + posB) * 0.5;
   Xf xA, xB; xA.o = posA - offset; xA.R = RA; xB.o = posB - offset; xB.R = RB;
-  V3 axis(0, 1, 0), pointOnA, pointOnB, normalInB;
+  V3 axis(0, 1, 0), pointOnA, pointOnB, normalInB, orgNormalInB;
   double sqd = 1e30, distance = 0;
   bool is_valid = false, check_simplex = false;
   int degenerate = 0, iter = 0;
@@ -642,9 +644,10 @@ PG_HDN bool closest_points(const Shape& sA, V3 posA, const M3& RA, const Shape& 
       pointOnB = pointOnB + axis * (mB / s);
       distance = (1.0 / rlen) - margin;
       is_valid = true;
+      orgNormalInB = normalInB;
     }
   }
-  bool catch_degenerate = degenerate && ((distance + margin) < 0.001);
+  bool catch_degenerate = degenerate && ((distance + margin) < PEN_TOL);
   if (!is_valid || catch_degenerate) {
     V3 tA, tB;
     axis = V3();
@@ -670,11 +673,17 @@ PG_HDN bool closest_points(const Shape& sA, V3 posA, const M3& RA, const Shape& 
   if (is_valid && (distance < 0 || distance * distance < max_dist2)) {
     V3 n = normalInB;
     V3 p = xf_apply(xA, support_core(sA, mulT(RA, -n))), q = xf_apply(xB, support_core(sB, mulT(RB, n)));
-    double d2 = dot(n, p - q) - margin;
+    double d0 = dot(n, p - q) - margin;
     V3 nn = -n;
     p = xf_apply(xA, support_core(sA, mulT(RA, -nn))); q = xf_apply(xB, support_core(sB, mulT(RB, nn)));
     double d1 = dot(nn, p - q) - margin;
-    if (d1 > d2) normalInB = -normalInB;
+    if (d1 > d0) normalInB = -normalInB;
+    if (len2(orgNormalInB) != 0) {            // the detector's last check: the GJK normal wins when it separates more than the EPA result
+      V3 no = orgNormalInB;
+      p = xf_apply(xA, support_core(sA, mulT(RA, -no))); q = xf_apply(xB, support_core(sB, mulT(RB, no)));
+      double d2 = dot(no, p - q) - margin;
+      if (d2 > d0 && d2 > d1 && d2 > distance) { normalInB = orgNormalInB; distance = d2; }
+    }
     normal_out = normalInB; point_b_out = pointOnB + offset; dist_out = distance;
     return true;
   }

@@ -69,6 +69,13 @@ PHYS = {  # exp: (rows to check, tolerance on pose) -- achieved tolerances, see 
 }
 
 
+# Bound over the WHOLE recorded horizon (100 substeps, both env steps) for the recordings that are followed to the end: the
+# north-star tolerance is 1e-4 on the object pose over the horizon.  cardboard / keyboard stay at rounding level; the plate (hull
+# object: GJK + EPA, whose double-precision tolerances REL_ERROR2 = gGjkEpaPenetrationTolerance = 1e-12 were found in round 2) stays
+# within 1e-5 (oracle and the kernel's host build: 9.1e-6).
+HORIZON = {"cardboard_20.0": 1e-11, "keyboard_20.0": 1e-11, "plate_20.0": 2e-5}
+
+
 # Env constants that changed in the reference AFTER a recording was made, identified from the recording itself: with the
 # committed cardboard env (floor lateralFriction 0.002, cardboard_contact_graph_env.py:193-194, under a "TODO: tune friction")
 # the first dragging substep is off by 1e-4; floor friction 0.005 reproduces the recorded displacement and rotation of that

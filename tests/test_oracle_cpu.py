@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import PHYS, RECORDING_TIME, ROOT, oracle_cost_spec, oracle_regions, oracle_spec, oracle_weights, recorded
+from helpers import HORIZON, PHYS, RECORDING_TIME, ROOT, oracle_cost_spec, oracle_regions, oracle_spec, oracle_weights, recorded
 from oracle import cost as CO
 from oracle import decode as D
 from oracle import dynfeas, mppi, scorenet
@@ -132,9 +132,42 @@ def test_physics_oracle_against_recorded_trajectories(exp):
         assert err[:13].max() <= 1e-12 and err[:18].max() <= 1.5e-8
     if exp == "plate_20.0":
         assert err[:7].max() <= 1e-10
-        assert err[:54].max() <= 1e-6 and err[:87].max() <= 2e-5 and err.max() <= 1e-3      # env step 2: within 2e-5 over 36 more substeps, 5e-4 over the whole horizon
+        assert err[:62].max() <= 1e-6 and err.max() <= 2e-5      # env step 2: within 1e-6 over 11 more substeps, 1e-5 over the whole horizon
     if exp == "cardboard_20.0":
         assert err[:70].max() <= 1e-12 and err.max() <= 1e-11          # the whole horizon at rounding level
+    if exp in HORIZON:
+        assert err.max() <= HORIZON[exp], err.max()
+
+
+@pytest.mark.parametrize("exp", sorted(PHYS))
+def test_product_kernel_logic_on_host_follows_recordings(exp):
+    """csrc/pg_rollout.cuh (the per-thread code of the CUDA kernel) compiled for the host, replaying the reference's recorded
+    controls: the same rows and bounds against the PyBullet recording as the oracle above (the GPU test repeats it on the device)."""
+    import dataclasses
+    so = os.path.join(ROOT, "tests", "hostsim", "libpg_hostsim.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-include", "cstdio",
+                           "-o", so, os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")])
+    H = C.CDLL(so)
+    g = recorded(exp)
+    spec = make_spec(g["env"])
+    ff = RECORDING_TIME.get(exp, {}).get("floor_friction")
+    if ff is not None:
+        spec = dataclasses.replace(spec, statics=[dataclasses.replace(b, friction=ff) if b.name == "floor" else b for b in spec.statics])
+    cs, keep = _abi.make_c_spec(spec)
+    N = 2
+    u = np.ascontiguousarray(g["u"], np.float64)
+    pose = np.zeros((1, N, 7)); fins = np.zeros((1, N, 2, 3)); metric = np.zeros(1); trace = np.zeros((1, N * 50, 7))
+    path = np.zeros(N, np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert H.hostsim_rollout(C.byref(cs), vp(u), None, 1, N, vp(path), C.c_double(g["max_force"]), 0, vp(pose), vp(fins), vp(metric),
+                             vp(trace), None) == 0
+    tr = trace[0]
+    e = np.minimum(np.abs(tr - g["poses"]), np.abs(tr * np.r_[1, 1, 1, -1, -1, -1, -1] - g["poses"])).max(axis=1)
+    rows, tol = PHYS[exp]
+    assert e[0] <= 1e-12, e[0]
+    assert e[list(rows)].max() <= tol, (e[list(rows)].max(), tol)
+    if exp in HORIZON:
+        assert e.max() <= HORIZON[exp], e.max()
 
 
 def test_physics_oracle_parked_fingertip_meets_idle_ones():
