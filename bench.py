@@ -362,6 +362,29 @@ def _src_sha16():
     return h.hexdigest()[:16]
 
 
+BOX_ROLLOUT_KERNEL = "_ZN2pg14rollout_kernelILi0EEEvPKNS_6EnvDevEPKdPKfiiPKidPdSA_SA_SA_PiS9_Pvi"      # pg::rollout_kernel<SHAPE_BOX>
+
+
+def _kernel_sass_sha16(mangled):
+    """sha256 over the SASS instruction lines of ONE kernel of the library being timed (cuobjdump -sass -fun): identifies the
+    machine code of that kernel -- an edit to a header that only another kernel compiles (pg_convex.cuh: hull objects) changes the
+    source hash but not this one.  None when cuobjdump is not on the box."""
+    import hashlib
+    import re
+    import shutil
+    import subprocess
+    from synthesize_pregrasp_b200 import _abi
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        out = subprocess.run([exe, "-sass", "-fun", mangled, _abi.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    lines = [ln for ln in out.splitlines() if re.match(r"^\s+/\*[0-9a-f]{4}\*/", ln)]
+    if not lines:
+        return None
+    return hashlib.sha256(("\n".join(lines) + "\n").encode()).hexdigest()[:16]
+
+
 def _fp64_peak():
     """Measured DFMA rate of the box (tools/ubench -> profiles/r2a_ubench.json), else the nominal 148 SM x 64 DFMA/clk."""
     p = os.path.join(ROOT, "profiles", "r2a_ubench.json")
@@ -378,7 +401,11 @@ def _ncu_traffic(workload):
         return None
     d = json.load(open(p))
     if d.get("src_sha16") != _src_sha16():
-        return None
+        # the sources changed since the capture: the figure still describes this build if the machine code of the captured kernel
+        # is the same (recorded next to the capture as kernel_sass_sha16)
+        want = d.get("kernel_sass_sha16", {}).get(workload)
+        if want is None or _kernel_sass_sha16(d.get("kernel", {}).get(workload, BOX_ROLLOUT_KERNEL)) != want:
+            return None
     return d.get("traffic_bytes", {}).get(workload)
 
 
@@ -524,7 +551,7 @@ def rollout_line(args, r, world, peaks):
             "note": "algorithmic HBM bytes are ~400 B per rollout-step (u, noise in; pose, fins, metric out), so this fraction is tiny by "
                     "construction: the kernel is bound by instruction issue / dependent-instruction latency of its fp64 code "
                     "(roofline_fp64; ncu evidence in profiles/README.md).  traffic = dram bytes of one launch from an ncu capture of "
-                    "this very build (profiles/ncu_traffic.json, matched by the sha256 of the library's sources), null when no such capture exists"}
+                    "this very build (profiles/ncu_traffic.json, matched by the sha256 of the library's sources or of the kernel's SASS), null when no such capture exists"}
     ach64 = FLOP_PER_SUBSTEP * r["substeps"] * K / (phys_ms * 1e-3) / 1e12
     roof64 = {"kernel": "rollout_kernel", "bound": "fp64-issue", "achieved": ach64, "peak": f64_peak, "unit": "TFLOP/s",
               "frac": ach64 / f64_peak, "peak_source": f64_src, "flop_per_substep": FLOP_PER_SUBSTEP,

@@ -28,7 +28,9 @@ sha = bench._src_sha16()
 out_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 out = json.load(open(out_path)) if os.path.exists(out_path) else {}
 if out.get("src_sha16") != sha:
-    out = {"src_sha16": sha, "traffic_bytes": {}, "duration": {}}
+    out = {"src_sha16": sha, "traffic_bytes": {}, "duration": {}, "kernel": {}, "kernel_sass_sha16": {}}
+out.setdefault("kernel", {})[workload] = bench.BOX_ROLLOUT_KERNEL        # the capture scripts profile box-object workloads
+out.setdefault("kernel_sass_sha16", {})[workload] = bench._kernel_sass_sha16(bench.BOX_ROLLOUT_KERNEL)
 out["traffic_bytes"][workload] = best[1]
 out["duration"][workload] = f"{best[0]} {best[2]}"
 json.dump(out, open(out_path, "w"), indent=1)

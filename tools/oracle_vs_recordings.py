@@ -38,6 +38,7 @@ for exp in PHYS:
     out[exp] = summary(run(exp))
 out["wall_laptop_20.0 + parked thumb collides with the idle fingertips (tip_idle_collide=1)"] = summary(run("wall_laptop_20.0", dict(tip_idle_collide=1)))
 out["keyboard_scale_20.0 + fingertip pairs off in env step 1 (its recorded thumb hovers)"] = summary(run("keyboard_scale_20.0", dict(tip_skip=3, tip_skip_n=48)))
+out["plate_20.0 with the single-precision GJK constants (REL_ERROR2 1e-6, penetration tolerance 1e-3, no GJK-normal check): the model before the last fix"] = summary(run("plate_20.0", dict(gjk_rel_error2=1e-6, gjk_pen_tol=1e-3, gjk_org_rule=0)))
 out["round-1 model for comparison (no idle fingertips, round-1 pair order, no pre-refresh)"] = {
     exp: summary(run(exp, dict(idle_tips=0, find_order=12345, marginal_rule=1, tt_never_early=0, compound_prerefresh=0)))["rows_within"] for exp in PHYS}
 print(json.dumps(out, indent=1))
