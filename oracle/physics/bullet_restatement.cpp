@@ -209,6 +209,7 @@ struct Params {
   int walls_first = 1;            // [H] this many (object, wall) pairs enter the pair cache before the early fingertip pairs: 1 (or 2)
                                   // carries waterbottle_20.0 from row 2 to row 20 (7e-8) and improves wall_laptop_20.0; 0 and 3 do not
   int force_iters = 0, force_step = 0;  // debugging: run exactly force_iters iterations at substep #force_step
+  double perturb = 0;             // debugging: added to the object's velocity (v.x and w.y) at step dbg_step -- measures how fast the trajectory amplifies a rounding-level difference
   int debug = 0;
 };
 
@@ -1245,6 +1246,7 @@ static void integrate(World& w) {
 
 static void step(World& w) {
   w.step_count++;
+  if (w.P.perturb != 0 && w.step_count == w.P.dbg_step && w.obj >= 0) { w.bodies[w.obj].v.x += w.P.perturb; w.bodies[w.obj].w.y += w.P.perturb; }
   collide(w);
   apply_external(w);
   solve(w);
@@ -1269,7 +1271,7 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(idle_order) S(tip_idle_order) S(tip_idle_collide) S(tt_never_early) S(compound_prerefresh) S(tipwall_order) S(drop_scan_reverse) S(marginal_rule) S(find_order) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(idle_order) S(tip_idle_order) S(tip_idle_collide) S(tt_never_early) S(compound_prerefresh) S(tipwall_order) S(drop_scan_reverse) S(marginal_rule) S(find_order) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(perturb) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }

@@ -32,14 +32,8 @@ def _oracle_trace(spec, u, noise_row, F, train=False):
 
 def _recording_time_spec(exp, env):
     """The env as it was when `exp` was recorded (tests/test_oracle_cpu.py RECORDING_TIME: constants identified from the data)."""
-    import dataclasses
-    from helpers import RECORDING_TIME
-    from synthesize_pregrasp_b200.envspec import make_spec
-    spec = make_spec(env)
-    ff = RECORDING_TIME.get(exp, {}).get("floor_friction")
-    if ff is not None:
-        spec = dataclasses.replace(spec, statics=[dataclasses.replace(b, friction=ff) if b.name == "floor" else b for b in spec.statics])
-    return spec
+    from helpers import recording_time_spec
+    return recording_time_spec(exp, env)
 
 
 @pytest.mark.parametrize("exp", ["plate_20.0", "waterbottle_20.0", "foodbox_20.0", "keyboard_20.0", "keyboard_scale_20.0", "wall_laptop_20.0", "cardboard_20.0"])

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import HORIZON, PHYS, RECORDING_TIME, ROOT, oracle_cost_spec, oracle_regions, oracle_spec, oracle_weights, recorded
+from helpers import HORIZON, PHYS, RECORDING_TIME, ROOT, recording_time_spec, oracle_cost_spec, oracle_regions, oracle_spec, oracle_weights, recorded
 from oracle import cost as CO
 from oracle import decode as D
 from oracle import dynfeas, mppi, scorenet
@@ -18,7 +18,7 @@ from synthesize_pregrasp_b200.envspec import ENV_NAMES, make_spec
 
 G = os.path.join(ROOT, "tests", "golden")
 DECODE_EXPS = ["plate_20.0", "foodbox_20.0", "foodbox_50.0", "keyboard_20.0", "keyboard_50.0", "wall_laptop_20.0",
-               "cardboard_20.0", "waterbottle_20.0"]
+               "cardboard_20.0", "waterbottle_20.0", "keyboard_scale_20.0"]
 
 
 def _qrot(q, v):
@@ -31,7 +31,7 @@ def _qrot(q, v):
 def test_decode_reproduces_recorded_tip_positions(exp):
     """data/tip_data/<exp>_tip_poses.npy = object pose o local contact point (model_test.py:124-135)."""
     g = recorded(exp)
-    spec = make_spec(g["env"])
+    spec = recording_time_spec(exp)
     reg = oracle_regions(spec, spec.dummy_states)
     carry = D.new_carry()
     from oracle.envsim import b3_multiply_transforms
@@ -108,13 +108,7 @@ def test_physics_oracle_against_recorded_trajectories(exp):
     """The only physics ground truth: data/object_poses/<exp>_object_poses.npy (PyBullet, recorded by model_test.py)."""
     from oracle.envsim import EnvSim
     g = recorded(exp)
-    spec = make_spec(g["env"])
-    osd = oracle_spec(spec)
-    if "floor_friction" in RECORDING_TIME.get(exp, {}):
-        i = osd["static_names"].index("floor")
-        half, pos, quat, _ = osd["statics"][i]
-        osd["statics"] = list(osd["statics"])
-        osd["statics"][i] = (half, pos, quat, RECORDING_TIME[exp]["floor_friction"])
+    osd = oracle_spec(recording_time_spec(exp))
     sim = EnvSim(osd, g["max_force"])
     sim.reset()
     P = np.concatenate([sim.step(g["u"][j], [0, 0, 0])["poses"] for j in range(2)])
@@ -143,16 +137,12 @@ def test_physics_oracle_against_recorded_trajectories(exp):
 def test_product_kernel_logic_on_host_follows_recordings(exp):
     """csrc/pg_rollout.cuh (the per-thread code of the CUDA kernel) compiled for the host, replaying the reference's recorded
     controls: the same rows and bounds against the PyBullet recording as the oracle above (the GPU test repeats it on the device)."""
-    import dataclasses
     so = os.path.join(ROOT, "tests", "hostsim", "libpg_hostsim.so")
     subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-include", "cstdio",
                            "-o", so, os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")])
     H = C.CDLL(so)
     g = recorded(exp)
-    spec = make_spec(g["env"])
-    ff = RECORDING_TIME.get(exp, {}).get("floor_friction")
-    if ff is not None:
-        spec = dataclasses.replace(spec, statics=[dataclasses.replace(b, friction=ff) if b.name == "floor" else b for b in spec.statics])
+    spec = recording_time_spec(exp)
     cs, keep = _abi.make_c_spec(spec)
     N = 2
     u = np.ascontiguousarray(g["u"], np.float64)
@@ -210,12 +200,22 @@ def test_idle_fingertips_timeline():
 
 
 def test_physics_oracle_resting_contact_exact():
-    """keyboard_scale_20.0 was recorded with another region table: its thumb hovers 1.2e-8 above the top face for the whole first
-    env step (ours, decoded by the committed env, overlaps by 1.1e-8), so PyBullet has no fingertip contact there.  With the
-    fingertip pairs switched off for that env step the restatement reproduces the recording at rounding level over 52 substeps of
-    resting contact on the floor (object vs compound floor: box-box, persistent manifold, per-island solve, slop, integration)."""
-    from oracle.envsim import EnvSim
+    """keyboard_scale_20.0 was recorded with another contact state (thumb on region 2; the committed dummy_states.npy says 9): its
+    thumb hovers 1.2e-8 above the top face for the whole first env step (the committed env's overlaps by 1.1e-8), so PyBullet has no
+    fingertip contact there.  (i) With the committed state and the fingertip pairs switched off for that env step the restatement
+    reproduces the recording at rounding level over 52 substeps of resting contact on the floor (object vs compound floor: box-box,
+    persistent manifold, per-island solve, slop, integration); (ii) with the recording-time state (helpers.RECORDING_TIME) the decoded
+    fingertip is the recorded one bit for bit and the WHOLE recording is reproduced at rounding level with nothing switched off."""
+    from oracle.envsim import EnvSim, b3_multiply_transforms
     g = recorded("keyboard_scale_20.0")
+    rt = recording_time_spec("keyboard_scale_20.0")
+    pos, on, _ = D.decode_step(g["u"][0], D.new_carry(), oracle_regions(rt, rt.dummy_states), [0, 0, 0], 0)
+    assert on[0] and not on[1]
+    assert np.array_equal(b3_multiply_transforms(g["poses"][0, :3], g["poses"][0, 3:], pos[0]), g["tips"][0, 0])
+    sim = EnvSim(oracle_spec(rt), g["max_force"])
+    sim.reset()
+    P = np.concatenate([sim.step(g["u"][j], [0, 0, 0])["poses"] for j in range(2)])
+    assert np.minimum(np.abs(P - g["poses"]), np.abs(P * np.r_[1, 1, 1, -1, -1, -1, -1] - g["poses"])).max() <= 1e-14
     # the recorded thumb does hover: its bottom face against the recorded top face, rows 0-49
     R22 = 1.0                                                # tilt 1e-7 rad: cos = 1 to 1e-14
     gap = (g["tips"][:50, 0, 2] - 0.01) - (g["poses"][:50, 2] + 0.03 * R22)

@@ -9,18 +9,14 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from helpers import PHYS, RECORDING_TIME, oracle_spec, recorded   # noqa: E402
+from helpers import PHYS, oracle_spec, recorded, recording_time_spec   # noqa: E402
 from oracle.envsim import EnvSim                                    # noqa: E402
 from synthesize_pregrasp_b200.envspec import make_spec             # noqa: E402
 
 
-def run(exp, params=None):
+def run(exp, params=None, committed_env=False):
     g = recorded(exp)
-    osd = oracle_spec(make_spec(g["env"]))
-    if "floor_friction" in RECORDING_TIME.get(exp, {}):
-        i = osd["static_names"].index("floor")
-        half, pos, quat, _ = osd["statics"][i]
-        osd["statics"] = list(osd["statics"]); osd["statics"][i] = (half, pos, quat, RECORDING_TIME[exp]["floor_friction"])
+    osd = oracle_spec(make_spec(g["env"]) if committed_env else recording_time_spec(exp))
     sim = EnvSim(osd, g["max_force"], params=params)
     sim.reset()
     P = np.concatenate([sim.step(g["u"][j], [0, 0, 0])["poses"] for j in range(2)])
@@ -37,7 +33,8 @@ out = {"note": "max abs pose error per recorded row (q == -q); rows_within[t] = 
 for exp in PHYS:
     out[exp] = summary(run(exp))
 out["wall_laptop_20.0 + parked thumb collides with the idle fingertips (tip_idle_collide=1)"] = summary(run("wall_laptop_20.0", dict(tip_idle_collide=1)))
-out["keyboard_scale_20.0 + fingertip pairs off in env step 1 (its recorded thumb hovers)"] = summary(run("keyboard_scale_20.0", dict(tip_skip=3, tip_skip_n=48)))
+out["keyboard_scale_20.0 with the COMMITTED dummy_states (thumb on region 9, where it touches; the recorded one, on region 2, hovers)"] = summary(run("keyboard_scale_20.0", committed_env=True))
+out["cardboard_20.0 with the COMMITTED floor friction 0.002 (recording time: 0.005)"] = summary(run("cardboard_20.0", committed_env=True))
 out["plate_20.0 with the single-precision GJK constants (REL_ERROR2 1e-6, penetration tolerance 1e-3, no GJK-normal check): the model before the last fix"] = summary(run("plate_20.0", dict(gjk_rel_error2=1e-6, gjk_pen_tol=1e-3, gjk_org_rule=0)))
 out["round-1 model for comparison (no idle fingertips, round-1 pair order, no pre-refresh)"] = {
     exp: summary(run(exp, dict(idle_tips=0, find_order=12345, marginal_rule=1, tt_never_early=0, compound_prerefresh=0)))["rows_within"] for exp in PHYS}
