@@ -426,3 +426,20 @@ def test_single_precision_multiply_transforms_native_equals_numpy_statement():
         p = rng.randn(3); q = rng.randn(4); q /= np.linalg.norm(q) * rng.uniform(0.999999, 1.000001)
         v = rng.randn(3) * rng.choice([1e-3, 0.1, 1.0, 100.0])
         np.testing.assert_array_equal(b3_multiply_transforms(p, q, v), b3_multiply_transforms_native(sim.L, p, q, v))
+
+
+def test_roofline_traffic_record_matches_this_build(built):
+    """bench.py reports roofline.traffic only for the build the ncu capture was taken from: matched by the hash of the library's
+    sources or -- when only a header that the captured kernel does not compile has changed -- by the hash of that kernel's SASS."""
+    import json
+    import shutil
+    import bench
+    rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    if shutil.which("cuobjdump") is None and not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sha = bench._kernel_sass_sha16(bench.BOX_ROLLOUT_KERNEL)
+    assert sha is not None and len(sha) == 16
+    assert bench._kernel_sass_sha16("_ZN2pg7no_suchEv") is None                      # unknown kernel -> no match, traffic null
+    for wl, want in rec.get("kernel_sass_sha16", {}).items():
+        assert (bench._ncu_traffic(wl) is not None) == (rec["src_sha16"] == bench._src_sha16() or want == sha)
+    assert bench._ncu_traffic("no_such_workload") is None
