@@ -1280,9 +1280,12 @@ void pgo_set_param(void* h, const char* name, double v) {
   if (!strcmp(name, "gjk_rel_error2")) { g_gjk_rel_error2 = v; return; }
   if (!strcmp(name, "gjk_pen_tol")) { g_gjk_pen_tol = v; return; }
   if (!strcmp(name, "gjk_org_rule")) { g_gjk_org_rule = (int)v; return; }
+  if (!strncmp(name, "cc_nudge", 8) && name[8] >= '0' && name[8] <= '6') { g_cc_nudge[name[8] - '0'] = v; return; }
   if (!strcmp(name, "bb_fudge")) { g_bb_fudge = v; return; }
   if (!strcmp(name, "bb_edge_point")) { g_bb_edge_point = (int)v; return; }
   if (!strcmp(name, "bb_edge_flip")) { g_bb_edge_flip = (int)v; return; }
+  if (!strcmp(name, "epa_accuracy")) { epa2::EPA_ACCURACY = v; return; }
+  if (!strcmp(name, "epa_plane_eps")) { epa2::EPA_PLANE_EPS = v; return; }
   if (!strcmp(name, "epa_variant")) { epa2::g_epa_variant = (int)v; return; }
   fprintf(stderr, "pgo_set_param: unknown %s\n", name);
 }

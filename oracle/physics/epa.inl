@@ -10,7 +10,7 @@ namespace epa2 {
 static const int GJK_MAX_ITERATIONS = 128;
 static const double GJK_ACCURACY = 1e-12, GJK_MIN_DISTANCE = 1e-12, GJK_DUPLICATED_EPS = 1e-12;
 static const int EPA_MAX_VERTICES = 128, EPA_MAX_ITERATIONS = 255, EPA_MAX_FACES = EPA_MAX_VERTICES * 2;
-static const double EPA_ACCURACY = 1e-12, EPA_PLANE_EPS = 1e-14;
+static double EPA_ACCURACY = 1e-12, EPA_PLANE_EPS = 1e-14;   // runtime for the what-if scans (Bullet, double precision: 1e-12 / 1e-14)
 
 static inline V3 vdiv(V3 a, double s) { return a * (1.0 / s); }        // btVector3::operator/ multiplies by the reciprocal
 
@@ -212,6 +212,7 @@ struct Gjk {
   }
 };
 
+static int g_epa_trace = 0;
 enum EpaStatus { EPA_VALID, EPA_TOUCHING, EPA_DEGENERATED, EPA_NONCONVEX, EPA_INVALIDHULL, EPA_OUTOFFACES, EPA_OUTOFVERTICES,
                  EPA_ACCURACYREACHED, EPA_FALLBACK, EPA_FAILED };
 
@@ -325,6 +326,7 @@ struct Epa {
             best->pass = (unsigned char)(++pass);
             gjk.getsupport(best->n, *w);
             double wdist = dot(best->n, w->w) - best->d;
+            if (g_epa_trace) fprintf(stderr, "    epa it %d best d %.15g wdist %.3e n %.9f %.9f %.9f\n", iterations, best->d, wdist, best->n.x, best->n.y, best->n.z);
             if (wdist > EPA_ACCURACY) {
               for (int j = 0; j < 3 && valid; ++j) valid &= expand(pass, w, best->f[j], best->e[j], horizon);
               if (valid && horizon.nf >= 3) {
@@ -336,6 +338,7 @@ struct Epa {
           } else { status = EPA_OUTOFVERTICES; break; }
         }
         V3 projection = outer.n * outer.d;
+        if (g_epa_trace) fprintf(stderr, "    epa final face edges %.3e %.3e %.3e\n", len(outer.c[1]->w - outer.c[0]->w), len(outer.c[2]->w - outer.c[1]->w), len(outer.c[0]->w - outer.c[2]->w));
         normal = outer.n; depth = outer.d;
         result.rank = 3; result.c[0] = outer.c[0]; result.c[1] = outer.c[1]; result.c[2] = outer.c[2];
         result.p[0] = len(cross(outer.c[1]->w - projection, outer.c[2]->w - projection));

@@ -15,6 +15,7 @@ static double g_pen_tie = 0.0;   // debugging: bias of the EPA-vs-GJK depth comp
 // plate_20.0 left the recording at row 87; with the double-precision values it stays within 1e-5 over all 100 rows).  The knobs
 // remain for the what-if runs of tools/oracle_vs_recordings.py.
 static double g_gjk_rel_error2 = 1.0e-12, g_gjk_pen_tol = 1.0e-12; static int g_gjk_org_rule = 1;
+static double g_cc_nudge[7] = {0, 0, 0, 0, 0, 0, 0};   // debugging: at step dbg_step, fingertip pairs: point += [0..2], distance += [3], normal += [4..6] (renormalised)
 
 static V3 support_core_local(const Shape& sh, V3 d) {
   if (sh.type == SH_BOX) {
@@ -223,7 +224,7 @@ static void convex_convex(World& w, Body& A, Body& B, ContactSink& out) {
   if (!is_valid || catch_degenerate) {
     // btGjkPairDetector penetration branch: EPA on the margin-inclusive shapes (epa.inl)
     g_epa_events++;
-    epa2::g_epa_debug = (w.P.debug > 1);
+    epa2::g_epa_debug = (w.P.debug > 1); epa2::g_epa_trace = (w.P.debug == 8 && w.step_count == w.P.dbg_step);
     V3 tA, tB;
     axis = V3();
     bool valid2 = epa2::calc_pen_depth(A.shape, A.R, oA, B.shape, B.R, oB, axis, tA, tB, pen_info);
@@ -264,6 +265,10 @@ static void convex_convex(World& w, Body& A, Body& B, ContactSink& out) {
     fprintf(stderr, "gjk step %d pair %d-%d iters %d degen %d n %d valid %d pen %d dist %.9g nrm %.6f %.6f %.6f pB %.6f %.6f %.6f\n", w.step_count,
             (int)(&A - &w.bodies[0]), (int)(&B - &w.bodies[0]), iter, degenerate, sx.n, (int)is_valid, pen_info, distance, normalInB.x, normalInB.y, normalInB.z,
             pointOnB.x + offset.x, pointOnB.y + offset.y, pointOnB.z + offset.z);
+  if (w.P.dbg_step > 0 && w.step_count == w.P.dbg_step && (&B - &w.bodies[0] == w.tip[0] || &A - &w.bodies[0] == w.tip[0] || &B - &w.bodies[0] == w.tip[1] || &A - &w.bodies[0] == w.tip[1])) {
+    pointOnB = pointOnB + V3(g_cc_nudge[0], g_cc_nudge[1], g_cc_nudge[2]); distance += g_cc_nudge[3];
+    normalInB = normalInB + V3(g_cc_nudge[4], g_cc_nudge[5], g_cc_nudge[6]); normalInB = normalInB / len(normalInB);
+  }
   if (is_valid && (distance < 0 || distance * distance < max_dist2))
     add_contact(out, normalInB, pointOnB + offset, distance);
   (void)w;
