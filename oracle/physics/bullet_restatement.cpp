@@ -175,6 +175,7 @@ struct Params {
   int pair_order_mode = -1;       // -1: by object type; 0: box-object order; 1: compound-object order (see collide)
   double tight_pad = 0.0;         // debugging: slack added to the tight-AABB test of compound children
   int order_step_min = 0;         // debugging: manifold_order3 applies from this step on
+  int manifold_order2 = 0, order_step_min2 = 1 << 30;   // debugging: a second explicit order (same coding as manifold_order >= 10000) from step order_step_min2 on
   int manifold_reverse = 0;       // debugging: reverse the final manifold order
   int manifold_order3 = 0;        // debugging: explicit order (digits, creation indices) when exactly 3 manifolds are solved
   int manifold_order = 0;         // 0: emulate quickSort of dispatcher order; k>=1: (k-1)-th permutation of creation order
@@ -209,6 +210,7 @@ struct Params {
   int walls_first = 1;            // [H] this many (object, wall) pairs enter the pair cache before the early fingertip pairs: 1 (or 2)
                                   // carries waterbottle_20.0 from row 2 to row 20 (7e-8) and improves wall_laptop_20.0; 0 and 3 do not
   int force_iters = 0, force_step = 0;  // debugging: run exactly force_iters iterations at substep #force_step
+  int idle_rel01 = 0, idle_rel02 = 0, idle_rel12 = 0;   // debugging: world step at which the idle fingertips' pair (i, j) leaves the pair cache (0: when its AABBs separate)
   double perturb = 0;             // debugging: added to the object's velocity (v.x and w.y) at step dbg_step -- measures how fast the trajectory amplifies a rounding-level difference
   int debug = 0;
 };
@@ -761,7 +763,17 @@ static void collide(World& w) {
   } else
   for (size_t i = 0; i < w.manifolds.size();) {
     Manifold& m = w.manifolds[i];
-    if (!pair_overlap(w, w.bodies[m.a], w.bodies[m.b])) { w.manifolds[i] = w.manifolds.back(); w.manifolds.pop_back(); }
+    bool gone = !pair_overlap(w, w.bodies[m.a], w.bodies[m.b]);
+    if (w.idle.size() == 3) {                    // debugging what-if: explicit release steps of the idle fingertips' pairs
+      auto ix = [&](int b) { for (int q = 0; q < 3; q++) if (w.idle[q] == b) return q; return -1; };
+      int qa = ix(m.a), qb = ix(m.b);
+      if (qa >= 0 && qb >= 0) {
+        int lo = std::min(qa, qb), hi = std::max(qa, qb);
+        int rel = (lo == 0 && hi == 1) ? w.P.idle_rel01 : (lo == 0 && hi == 2) ? w.P.idle_rel02 : w.P.idle_rel12;
+        if (rel > 0) gone = w.step_count >= rel;
+      }
+    }
+    if (gone) { w.manifolds[i] = w.manifolds.back(); w.manifolds.pop_back(); }
     else i++;
   }
   // new pairs.  Creation order emulates the order in which Bullet's broadphase reports the object's
@@ -846,6 +858,15 @@ static void collide(World& w) {
     }
     if (!pair_overlap(w, bi, bj)) continue;
     if (find_manifold(w, i, j)) continue;
+    if (w.idle.size() == 3 && (w.P.idle_rel01 || w.P.idle_rel02 || w.P.idle_rel12)) {
+      auto ix = [&](int b) { for (int q = 0; q < 3; q++) if (w.idle[q] == b) return q; return -1; };
+      int qa = ix(i), qb = ix(j);
+      if (qa >= 0 && qb >= 0) {
+        int lo = std::min(qa, qb), hi = std::max(qa, qb);
+        int rel = (lo == 0 && hi == 1) ? w.P.idle_rel01 : (lo == 0 && hi == 2) ? w.P.idle_rel02 : w.P.idle_rel12;
+        if (rel > 0 && w.step_count >= rel) continue;
+      }
+    }
     if (w.P.dbg_skip_new > 0 && w.step_count == w.P.dbg_skip_new && (bi.compound || bj.compound)) continue;   // debugging what-if
     Manifold m;
     if (bi.compound) { m.a = i; m.b = j; }
@@ -1102,7 +1123,7 @@ static void solve(World& w) {
     } else if (P.manifold_order >= 10000 && mlist.size() > 1 && w.step_count >= P.order_step_min) {
       // explicit order: digits of (manifold_order - 10000), zero padded to mlist.size(), index creation order
       std::sort(mlist.begin(), mlist.end());
-      std::vector<int> src = mlist; int code = P.manifold_order - 10000; int n = (int)src.size();
+      std::vector<int> src = mlist; int code = (w.step_count >= P.order_step_min2 ? P.manifold_order2 : P.manifold_order) - 10000; int n = (int)src.size();
       for (int k = n - 1; k >= 0; k--) { int dgt = code % 10; code /= 10; if (dgt < n) mlist[k] = src[dgt]; }
     } else if (P.manifold_order > 0 && P.manifold_order < 10000 && mlist.size() > 1) {
       std::sort(mlist.begin(), mlist.end());
@@ -1271,7 +1292,7 @@ void pgo_set_param(void* h, const char* name, double v) {
 #define S(n) if (!strcmp(name, #n)) { P.n = (decltype(P.n))v; return; }
   S(dt) S(gravity_z) S(iterations) S(erp) S(erp2) S(linear_slop) S(warmstart) S(residual_threshold)
   S(lin_damping) S(ang_damping) S(gyro) S(cone_friction) S(two_dirs) S(breaking_factor) S(aabb_margin) S(tight_pad)
-  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(idle_order) S(tip_idle_order) S(tip_idle_collide) S(tt_never_early) S(compound_prerefresh) S(tipwall_order) S(drop_scan_reverse) S(marginal_rule) S(find_order) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(perturb) S(debug)
+  S(max_coord_vel) S(manifold_order) S(manifold_order3) S(manifold_reverse) S(order_step_min) S(manifold_order2) S(order_step_min2) S(pair_order_mode) S(constraint_reverse) S(residual_max) S(merge_islands) S(force_iters) S(force_step) S(pair_flip) S(dbg_skip_new) S(pos_variant) S(cone_variant) S(tip_skip) S(tip_skip_n) S(idle_order) S(tip_idle_order) S(tip_idle_collide) S(tt_never_early) S(compound_prerefresh) S(tipwall_order) S(drop_scan_reverse) S(marginal_rule) S(find_order) S(fs_idx0) S(fs_idx1) S(fs_val0) S(fs_val1) S(skip_body) S(skip_other) S(pos_drop) S(fric_scale) S(dbg_step) S(dbg_idx) S(walls_first) S(default_max_impulse) S(perturb) S(idle_rel01) S(idle_rel02) S(idle_rel12) S(debug)
 #undef S
   if (!strcmp(name, "hull_aabb_margins")) { g_hull_aabb_margins = v; return; }
   if (!strcmp(name, "compound_margin")) { g_compound_margin = v; return; }
