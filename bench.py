@@ -480,13 +480,18 @@ def measure_rollouts(args, name, wl, steps, warmup, rank, world, local, cpu_seco
     launches = int(L.pg_launch_count() - l0)
     total_ms = ev[0].elapsed_time(ev[-1])
     # dominant-kernel timing: physics and cost stages separately, CUDA events on the launching stream
+    # (median of three samples: a single launch scatters by several per cent; one sample for the very large jobs)
     out = eng.physics(u, noise, path, wl["force"])
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    torch.cuda.synchronize()
-    e0.record(); out = eng.physics(u, noise, path, wl["force"]); e1.record()
-    eng.cost(out["pose"], out["fins"]); e2.record()
-    torch.cuda.synchronize()
-    phys_ms, cost_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    samples = []
+    for _ in range(3 if K <= (1 << 17) else 1):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        torch.cuda.synchronize()
+        e0.record(); out = eng.physics(u, noise, path, wl["force"]); e1.record()
+        eng.cost(out["pose"], out["fins"]); e2.record()
+        torch.cuda.synchronize()
+        samples.append((e0.elapsed_time(e1), e1.elapsed_time(e2)))
+    phys_ms = sorted(s[0] for s in samples)[len(samples) // 2]
+    cost_ms = sorted(s[1] for s in samples)[len(samples) // 2]
     # e2e: host buffers in, host J out, through the plugin-facing C-ABI call
     nh = noise_host.numpy(); uh = np.zeros((N_STEPS, D))
     if K <= (1 << 17):
