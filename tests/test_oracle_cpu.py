@@ -270,7 +270,8 @@ def test_product_kernel_logic_on_host_matches_oracle():
                            "-o", so, os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")])
     H = C.CDLL(so)
     rng = np.random.RandomState(7)
-    for env, F in (("keyboard", 20.0), ("bookshelf", 50.0), ("laptop", 20.0), ("plate", 20.0), ("waterbottle", 20.0)):
+    for env, F in (("keyboard", 20.0), ("bookshelf", 50.0), ("laptop", 20.0), ("plate", 20.0), ("waterbottle", 20.0),
+                   ("foodbox", 20.0), ("cardboard", 20.0)):
         spec = make_spec(env)
         cs, keep = _abi.make_c_spec(spec)
         u = 0.8 * rng.randn(2, 48)
