@@ -18,7 +18,7 @@ from synthesize_pregrasp_b200.envspec import ENV_NAMES, make_spec
 
 G = os.path.join(ROOT, "tests", "golden")
 DECODE_EXPS = ["plate_20.0", "foodbox_20.0", "foodbox_50.0", "keyboard_20.0", "keyboard_50.0", "wall_laptop_20.0",
-               "cardboard_20.0", "waterbottle_20.0", "keyboard_scale_20.0"]
+               "cardboard_20.0", "waterbottle_20.0", "keyboard_scale_20.0", "cardboard_scale_20.0", "cardboard2_20.0", "cardboard3_20.0"]
 
 
 def _qrot(q, v):
@@ -131,6 +131,22 @@ def test_physics_oracle_against_recorded_trajectories(exp):
         assert err[:70].max() <= 1e-12 and err.max() <= 1e-11          # the whole horizon at rounding level
     if exp in HORIZON:
         assert err.max() <= HORIZON[exp], err.max()
+
+
+@pytest.mark.parametrize("exp", ["cardboard2_20.0", "cardboard3_20.0"])
+def test_held_out_recordings_second_env_step_is_a_pair_order(exp):
+    """The two held-out recordings whose thumb stays on the plate through both env steps are exact over env step 1 with the frozen
+    model and leave it in the first substep of env step 2 (7e-6 / 3e-6).  One thing explains both: there the re-created object proxy
+    finds the thumb BEFORE the floor (oracle knob find_order_late = 3429) -- with it all 100 rows are reproduced at 2e-12 / 2e-11.  The
+    model does not adopt it as a rule: keyboard_scale_20.0 (thumb on in both env steps as well) needs the floor first, i.e. the order
+    follows Bullet's broadphase tree (re-sorted by node address), which can be fitted per recording but not derived."""
+    from oracle.envsim import EnvSim
+    g = recorded(exp)
+    sim = EnvSim(oracle_spec(recording_time_spec(exp)), g["max_force"], params=dict(find_order_late=3429))
+    sim.reset()
+    P = np.concatenate([sim.step(g["u"][j], [0, 0, 0])["poses"] for j in range(2)])
+    err = np.minimum(np.abs(P - g["poses"]), np.abs(P * np.r_[1, 1, 1, -1, -1, -1, -1] - g["poses"])).max()
+    assert err <= 1e-10, err
 
 
 @pytest.mark.parametrize("exp", sorted(PHYS))

@@ -141,7 +141,10 @@ def gen_mppi(rng):
 def gen_recorded():
     exps = {"plate_20.0": "plate", "foodbox_20.0": "foodbox", "foodbox_50.0": "foodbox", "keyboard_20.0": "keyboard",
             "keyboard_50.0": "keyboard", "keyboard_scale_20.0": "keyboard", "wall_laptop_20.0": "laptop",
-            "cardboard_20.0": "cardboard", "waterbottle_20.0": "waterbottle", "book_shelf_50.0": "bookshelf"}
+            "cardboard_20.0": "cardboard", "waterbottle_20.0": "waterbottle", "book_shelf_50.0": "bookshelf",
+            # held out until the physics model was frozen (end of round 2), then replayed without touching it:
+            "cardboard_scale_20.0": "cardboard", "cardboard2_20.0": "cardboard", "cardboard3_20.0": "cardboard",
+            "foodbox_ablation_df_20.0": "foodbox"}
     out = {}
     for exp, env in exps.items():
         k = exp.replace(".", "p")

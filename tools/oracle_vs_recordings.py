@@ -36,6 +36,8 @@ out["wall_laptop_20.0 + parked thumb collides with the idle fingertips (tip_idle
 out["keyboard_scale_20.0 with the COMMITTED dummy_states (thumb on region 9, where it touches; the recorded one, on region 2, hovers)"] = summary(run("keyboard_scale_20.0", committed_env=True))
 out["cardboard_20.0 with the COMMITTED floor friction 0.002 (recording time: 0.005)"] = summary(run("cardboard_20.0", committed_env=True))
 out["plate_20.0 with the single-precision GJK constants (REL_ERROR2 1e-6, penetration tolerance 1e-3, no GJK-normal check): the model before the last fix"] = summary(run("plate_20.0", dict(gjk_rel_error2=1e-6, gjk_pen_tol=1e-3, gjk_org_rule=0)))
+out["cardboard2_20.0 (held out) with the thumb found before the floor in env step 2 (find_order_late=3429)"] = summary(run("cardboard2_20.0", dict(find_order_late=3429)))
+out["cardboard3_20.0 (held out) with the thumb found before the floor in env step 2 (find_order_late=3429)"] = summary(run("cardboard3_20.0", dict(find_order_late=3429)))
 out["round-1 model for comparison (no idle fingertips, round-1 pair order, no pre-refresh)"] = {
     exp: summary(run(exp, dict(idle_tips=0, find_order=12345, marginal_rule=1, tt_never_early=0, compound_prerefresh=0)))["rows_within"] for exp in PHYS}
 print(json.dumps(out, indent=1))
