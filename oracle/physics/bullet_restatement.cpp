@@ -200,10 +200,11 @@ struct Params {
   int tip_idle_order = 0;         // order of a parked fingertip's pairs with the idle ones: 0 ascending, 1 descending, -1: found last (generic)
   int idle_order = 0;             // creation order of the idle fingertips' pairs: 0: (2,3),(2,4),(3,4); 1: (2,3),(3,4),(2,4)
   int find_order = 4239;          // [H] order in which the re-created object proxy finds its pairs: digits 4 compound floor, 2 index tip, 3 thumb (tips whose tight AABB overlapped), 9 walls youngest first (1 / 5 / 6-8: round-1 and per-wall variants)
-  int find_order_late = 0;        // what-if: find order of a BOX object's re-created proxy in every env step after the first (world step > 52).
-                                  // cardboard2_20.0 / cardboard3_20.0 (thumb on the plate in both env steps) want the thumb BEFORE the
-                                  // floor there (3429: exact over all 100 rows instead of 51), keyboard_scale_20.0 (thumb on in both env
-                                  // steps too) wants it after: the order follows the broadphase tree, not a rule of the env
+  int find_order_late = 0;        // what-if: find order of the object's re-created proxy in every env step after the first (world step > 52).
+                                  // The held-out cardboard2_20.0 / cardboard3_20.0 (thumb on the plate in both env steps) and plate_no_df_20.0
+                                  // (thumb new in env step 2) want the thumb BEFORE the floor there (3429: all 100 rows instead of 51),
+                                  // keyboard_scale_20.0 and plate_20.0 want the floor first: the order follows the broadphase tree of the
+                                  // moment, not a rule of the env
   int find_order2 = 0, find_order2_min = 1 << 30;   // what-if: another find order from world step find_order2_min on
   int fs_idx0 = -1, fs_idx1 = -1; double fs_val0 = 1, fs_val1 = 1;
   int tip_skip_n = 0;             // ... and for this many further steps
@@ -829,7 +830,7 @@ static void collide(World& w) {
     {
       int digits[8], nd = 0;
       int fo = w.P.find_order;
-      if (w.P.find_order_late > 0 && w.step_count > 52 && w.bodies[w.obj].shape.type == SH_BOX && !w.bodies[w.obj].compound) fo = w.P.find_order_late;
+      if (w.P.find_order_late > 0 && w.step_count > 52) fo = w.P.find_order_late;
       if (w.P.find_order2 > 0 && w.step_count >= w.P.find_order2_min) fo = w.P.find_order2;
       for (int c = fo; c > 0; c /= 10) digits[nd++] = c % 10;
       for (int q = nd - 1; q >= 0; q--) {

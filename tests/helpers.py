@@ -73,8 +73,11 @@ PHYS = {  # exp: (rows to check, tolerance on pose) -- achieved tolerances, see 
     "cardboard2_20.0": (range(0, 51), 1e-10),             # all of env step 1 (2e-12); env step 2 needs the thumb found before the floor
     "cardboard3_20.0": (range(0, 51), 1e-10),             # all of env step 1 (7e-12); (oracle knob find_order_late: then 100 rows at 2e-11)
     "foodbox_ablation_df_20.0": (range(0, 100), 1e-12),   # both fingertips off in both env steps: resting contact, whole recording
+    "plate_ablation_df_20.0": (range(0, 51), 5e-8),       # the north-star task, another trajectory: env step 1 at 1e-8, whole recording 1.3e-5
+    "plate_no_df_20.0": (range(0, 51), 1e-8),             # all of env step 1 (2e-10); env step 2: thumb before floor -> 100 rows at 2e-8
 }
-HELD_OUT = ("cardboard_scale_20.0", "cardboard2_20.0", "cardboard3_20.0", "foodbox_ablation_df_20.0")
+HELD_OUT = ("cardboard_scale_20.0", "cardboard2_20.0", "cardboard3_20.0", "foodbox_ablation_df_20.0", "plate_ablation_df_20.0",
+            "plate_no_df_20.0")
 
 
 # Bound over the WHOLE recorded horizon (100 substeps, both env steps) for the recordings that are followed to the end: the
@@ -82,7 +85,7 @@ HELD_OUT = ("cardboard_scale_20.0", "cardboard2_20.0", "cardboard3_20.0", "foodb
 # object: GJK + EPA, whose double-precision tolerances REL_ERROR2 = gGjkEpaPenetrationTolerance = 1e-12 were found in round 2) stays
 # within 1e-5 (oracle and the kernel's host build: 9.1e-6).
 HORIZON = {"cardboard_20.0": 1e-11, "keyboard_20.0": 1e-11, "keyboard_scale_20.0": 1e-11, "plate_20.0": 2e-5,
-           "cardboard_scale_20.0": 1e-8, "foodbox_ablation_df_20.0": 1e-12}
+           "cardboard_scale_20.0": 1e-8, "foodbox_ablation_df_20.0": 1e-12, "plate_ablation_df_20.0": 5e-5}
 
 
 # Env constants that changed in the reference AFTER a recording was made, identified from the recording itself: with the
@@ -102,7 +105,8 @@ HORIZON = {"cardboard_20.0": 1e-11, "keyboard_20.0": 1e-11, "keyboard_scale_20.0
 RECORDING_TIME = {"cardboard_20.0": {"floor_friction": 0.005}, "keyboard_scale_20.0": {"state0_thumb_region": 2},
                   "cardboard_scale_20.0": {"state0_thumb_region": 1},
                   "cardboard2_20.0": {"state0_thumb_region": 9, "floor_friction": 0.005},
-                  "cardboard3_20.0": {"state0_thumb_region": 6}}
+                  "cardboard3_20.0": {"state0_thumb_region": 6},
+                  "plate_no_df_20.0": {"state0_thumb_region": 33, "state0_index_region": 54}}   # committed plate state 0: (48, 30)
 
 
 def recording_time_spec(exp, env=None):
@@ -113,8 +117,9 @@ def recording_time_spec(exp, env=None):
     if "floor_friction" in rt:
         spec = dataclasses.replace(spec, statics=[dataclasses.replace(b, friction=rt["floor_friction"]) if b.name == "floor" else b
                                                   for b in spec.statics])
-    if "state0_thumb_region" in rt:
+    if "state0_thumb_region" in rt or "state0_index_region" in rt:
         st = np.array(spec.dummy_states).copy()
-        st[0, 0] = rt["state0_thumb_region"]
+        st[0, 0] = rt.get("state0_thumb_region", st[0, 0])
+        st[0, 1] = rt.get("state0_index_region", st[0, 1])
         spec = dataclasses.replace(spec, dummy_states=st)
     return spec

@@ -38,7 +38,8 @@ def _recording_time_spec(exp, env):
 
 @pytest.mark.parametrize("exp", ["plate_20.0", "waterbottle_20.0", "foodbox_20.0", "keyboard_20.0", "keyboard_scale_20.0", "wall_laptop_20.0", "cardboard_20.0",
                                  # held-out recordings (tests/helpers.py HELD_OUT): replayed with the frozen model
-                                 "cardboard_scale_20.0", "cardboard2_20.0", "cardboard3_20.0", "foodbox_ablation_df_20.0"])
+                                 "cardboard_scale_20.0", "cardboard2_20.0", "cardboard3_20.0", "foodbox_ablation_df_20.0",
+                                 "plate_ablation_df_20.0", "plate_no_df_20.0"])
 def test_physics_kernel_on_recorded_controls(EN, exp):
     """K=1 replay of the reference's recorded u: kernel vs oracle (tight) and vs the PyBullet recording over the SAME rows and
     tolerances the oracle itself is held to (tests/test_oracle_cpu.py PHYS)."""

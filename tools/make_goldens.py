@@ -144,7 +144,7 @@ def gen_recorded():
             "cardboard_20.0": "cardboard", "waterbottle_20.0": "waterbottle", "book_shelf_50.0": "bookshelf",
             # held out until the physics model was frozen (end of round 2), then replayed without touching it:
             "cardboard_scale_20.0": "cardboard", "cardboard2_20.0": "cardboard", "cardboard3_20.0": "cardboard",
-            "foodbox_ablation_df_20.0": "foodbox"}
+            "foodbox_ablation_df_20.0": "foodbox", "plate_ablation_df_20.0": "plate", "plate_no_df_20.0": "plate"}
     out = {}
     for exp, env in exps.items():
         k = exp.replace(".", "p")
