@@ -134,7 +134,7 @@ def test_physics_oracle_against_recorded_trajectories(exp):
         assert err.max() <= HORIZON[exp], err.max()
 
 
-@pytest.mark.parametrize("exp", ["cardboard2_20.0", "cardboard3_20.0", "plate_no_df_20.0"])
+@pytest.mark.parametrize("exp", ["cardboard2_20.0", "cardboard3_20.0", "plate_no_df_20.0", "plate_ablation_df_20.0"])
 def test_held_out_recordings_second_env_step_is_a_pair_order(exp):
     """The two held-out recordings whose thumb stays on the plate through both env steps are exact over env step 1 with the frozen
     model and leave it in the first substep of env step 2 (7e-6 / 3e-6).  One thing explains both: there the re-created object proxy
@@ -147,7 +147,8 @@ def test_held_out_recordings_second_env_step_is_a_pair_order(exp):
     sim.reset()
     P = np.concatenate([sim.step(g["u"][j], [0, 0, 0])["poses"] for j in range(2)])
     err = np.minimum(np.abs(P - g["poses"]), np.abs(P * np.r_[1, 1, 1, -1, -1, -1, -1] - g["poses"])).max()
-    assert err <= (5e-8 if exp.startswith("plate") else 1e-10), err      # (plate_no_df_20.0: thumb new in env step 2; 2.3e-8)
+    # (plate_no_df_20.0: thumb new in env step 2, 2.3e-8; plate_ablation_df_20.0: 3.9e-11 instead of the frozen model's 1.3e-5)
+    assert err <= {"plate_no_df_20.0": 5e-8, "plate_ablation_df_20.0": 1e-9}.get(exp, 1e-10), err
 
 
 @pytest.mark.parametrize("exp", sorted(PHYS))

@@ -39,6 +39,7 @@ out["plate_20.0 with the single-precision GJK constants (REL_ERROR2 1e-6, penetr
 out["cardboard2_20.0 (held out) with the thumb found before the floor in env step 2 (find_order_late=3429)"] = summary(run("cardboard2_20.0", dict(find_order_late=3429)))
 out["cardboard3_20.0 (held out) with the thumb found before the floor in env step 2 (find_order_late=3429)"] = summary(run("cardboard3_20.0", dict(find_order_late=3429)))
 out["plate_no_df_20.0 (held out) with the thumb found before the floor in env step 2 (find_order_late=3429)"] = summary(run("plate_no_df_20.0", dict(find_order_late=3429)))
+out["plate_ablation_df_20.0 (held out) with the thumb found before the floor in env step 2 (find_order_late=3429)"] = summary(run("plate_ablation_df_20.0", dict(find_order_late=3429)))
 out["round-1 model for comparison (no idle fingertips, round-1 pair order, no pre-refresh)"] = {
     exp: summary(run(exp, dict(idle_tips=0, find_order=12345, marginal_rule=1, tt_never_early=0, compound_prerefresh=0)))["rows_within"] for exp in PHYS}
 print(json.dumps(out, indent=1))
