@@ -1,9 +1,9 @@
 // Convex-convex narrowphase for hull objects (the plate env): one closest-point / penetration query per pair and
 // substep, with the semantics of Bullet's btConvexConvexAlgorithm (reference: envs/plate_contact_graph_env.py:198
 // loads plate_cvx_simple.urdf, whose mesh becomes a btConvexHullShape inside a btCompoundShape).
-//   * separated cores: GJK on the margin-less shapes with a Voronoi-region simplex solver, margins added back
-//   * core distance below 1 mm or overlapping cores: expanding-polytope penetration query on the margin-inclusive
-//     shapes, nine guess directions
+//   * separated cores: GJK on the margin-less shapes with a Voronoi-region simplex solver (double-precision tolerances), margins added back
+//   * overlapping cores (degenerate simplex within 1e-12): expanding-polytope penetration query on the margin-inclusive
+//     shapes, nine guess directions; the detector's final normal checks (d0 / d1, and the GJK normal when it separates more)
 // Index-based pools and explicit stacks (no recursion, no pointers) so one thread can run it out of local memory.
 // Written after bullet3's published btGjkPairDetector / btVoronoiSimplexSolver / btGjkEpa2 (zlib licence, (c) Erwin Coumans,
 // Nathanael Presson et al.): bit-level parity with that engine requires its thresholds and operation order.
