@@ -1398,6 +1398,13 @@ void pgo_get_pose(void* h, int body, double* out7) {
   Body& b = ((World*)h)->bodies[body];
   out7[0] = b.pos.x; out7[1] = b.pos.y; out7[2] = b.pos.z; out7[3] = b.q.x; out7[4] = b.q.y; out7[5] = b.q.z; out7[6] = b.q.w;
 }
+// the body's AABB as btCollisionWorld::updateSingleAabb would pass it to the broadphase (extra = 0.02) or as refreshBroadphaseProxy does
+// (extra = 0): used by tools/whatif/dbvt_find_order.py
+void pgo_get_aabb(void* h, int body, double extra, double* out6) {
+  World& w = *(World*)h; Body b = w.bodies[body];
+  update_cache(b); compute_aabb(b, extra);
+  out6[0] = b.aabb_lo.x; out6[1] = b.aabb_lo.y; out6[2] = b.aabb_lo.z; out6[3] = b.aabb_hi.x; out6[4] = b.aabb_hi.y; out6[5] = b.aabb_hi.z;
+}
 void pgo_get_vel(void* h, int body, double* out6) {
   Body& b = ((World*)h)->bodies[body];
   out6[0] = b.v.x; out6[1] = b.v.y; out6[2] = b.v.z; out6[3] = b.w.x; out6[4] = b.w.y; out6[5] = b.w.z;
