@@ -139,6 +139,10 @@ class Dbvt:
         return out
 
 
+RESET_UPDATES_AABB = int(os.environ.get("RESET_UPDATES_AABB", "0"))
+REVERSE_OBJECTS = int(os.environ.get("REVERSE_OBJECTS", "0"))
+
+
 class Mirror:
     """ctypes-library proxy: forwards every call to the oracle and mirrors the broadphase side effects into a Dbvt"""
 
@@ -172,8 +176,15 @@ class Mirror:
         if self.nstep > 0:                               # (the filter calls of reset() happen before the proxies matter)
             self._recreate(h, a); self._recreate(h, b)
 
+    def pgo_reset_pose(self, h, b, pos, quat):
+        self.L.pgo_reset_pose(h, b, pos, quat)
+        if RESET_UPDATES_AABB:                           # resetBasePositionAndOrientation -> updateSingleAabb (teleport)
+            lo, hi = self._aabb(h, b, self.m)
+            if not _contain(self.leaf[b], lo, hi):
+                self.t.update(self.leaf[b], lo, hi)
+
     def pgo_step(self, h):
-        for b in sorted(self.leaf):                      # updateAabbs, collision-object order; gDbvtMargin = 0
+        for b in sorted(self.leaf, reverse=bool(REVERSE_OBJECTS)):   # updateAabbs, collision-object order; gDbvtMargin = 0
             lo, hi = self._aabb(h, b, self.m)
             lf = self.leaf[b]
             if not _contain(lf, lo, hi):
